@@ -1,0 +1,86 @@
+"""ctypes loader for the C-ABI shared library ``libbyol_b200.so`` (declared in ``include/byol_b200.h``).
+
+There is deliberately NO fallback: if the library is missing or a symbol cannot be resolved the import of
+any product module fails loudly.  Build it with ``python -c "import __graft_entry__ as g; g.build()"`` (or
+``make -C byol_b200/csrc``).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbyol_b200.so")
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_int64 = ctypes.c_int64
+c_float = ctypes.c_float
+c_double = ctypes.c_double
+
+# name -> argtypes (all functions return int status unless listed in _SPECIAL)
+_SIGNATURES = {
+    "byol_conv_igemm": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,  # src wt dst resid bias col_sum col_sqsum
+                        c_int, c_int, c_int, c_int, c_int, c_int, c_int,                      # Nimg Hs Ws C Ho Wo Ndim
+                        c_int, c_int, c_int, c_int, c_int, c_int, c_int,                      # KH KW stride pad mode ldw ldc
+                        c_int, c_int, c_int, c_void_p],                                        # out_fp32 relu force_gather stream
+    "byol_conv_wgrad": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                        c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "byol_bn_stats": [c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "byol_bn_finalize": [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p,
+                         c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "byol_bn_eval_coeffs": [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p],
+    "byol_bn_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                      c_int, c_void_p],
+    "byol_bn_bwd_reduce": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                           c_int, c_int, c_void_p],
+    "byol_bn_bwd_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_double, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "byol_col_sum": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "byol_nchw_to_nhwc8": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "byol_prep_weight": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "byol_cast_f32_bf16": [c_void_p, c_void_p, c_int64, c_void_p],
+    "byol_maxpool_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "byol_maxpool_bwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "byol_avgpool_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "byol_avgpool_bwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "byol_loss_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "byol_loss_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                      c_void_p],
+    "byol_ema_update": [c_void_p, c_void_p, c_float, c_float, c_int64, c_void_p],
+    "byol_lars_sgd_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                           c_void_p, c_int, c_void_p, c_float, c_float, c_float, c_int, c_void_p],
+    "byol_abi_version": [],
+    "byol_device_sm_count": [],
+}
+
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES.keys()) + ["byol_last_error"])
+
+
+class ByolLibraryError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "byol_b200: %s not found. The CUDA extension is mandatory (no CPU / PyTorch fallback exists). "
+            "Build it with `python -c 'import __graft_entry__ as g; g.build()'` from the repository root." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing: loud by design
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    lib.byol_last_error.argtypes = []
+    lib.byol_last_error.restype = ctypes.c_char_p
+    return lib
+
+
+lib = _load()
+
+
+def last_error():
+    return lib.byol_last_error().decode("utf-8", "replace")
+
+
+def check(status, what):
+    if status != 0:
+        raise ByolLibraryError("%s failed (status %d): %s" % (what, status, last_error()))

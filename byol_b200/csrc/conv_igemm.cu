@@ -1,0 +1,683 @@
+// byol_b200 — implicit-GEMM convolution / linear layers on tcgen05 tensor cores (sm_100a).
+//
+// Replaces the cuDNN conv fwd/dgrad/wgrad and cuBLAS Linear calls reached from the reference at
+// /root/reference/main.py:229-240 (BYOL.prediction: base_network -> head -> predictor).
+//
+// Data layout: activations NHWC bf16 (channels padded to a multiple of 8), weights bf16
+// [Cout][KH*KW*Cin] K-major (prepared from the fp32 master by byol_prep_weight).
+//
+//   out[m, n] = sum_{tap, c} src[pix(m, tap), c] * Wt[n, tap*C + c]          (fprop and dgrad)
+//   dW[n, tap, c] += sum_m dY[m, n] * src[pix(m, tap), c]                     (wgrad)
+//
+// One CTA computes a 128 x BN tile.  Warp roles:
+//   warps 0-3 : A-operand gather (cp.async 16 B, zero-fill for padding) and, later, the epilogue
+//               (tcgen05.ld TMEM -> registers -> global)
+//   warp 4    : TMEM allocation + single-thread tcgen05.mma issue
+//   warp 5    : barrier init + TMA producer (weights always; activations when the conv is a
+//               plain GEMM, i.e. 1x1 stride 1 / Linear)
+// smem operand tiles use the 128-byte swizzle; accumulators live in TMEM.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace byol {
+
+static constexpr int BM = 128;           // output rows (pixels) per CTA
+static constexpr int BK = 64;            // bf16 elements per k-block (= one 128-byte swizzle row)
+static constexpr int A_STAGE_BYTES = BM * 128;
+static constexpr int GATHER_LAG = 2;     // cp.async groups in flight per producer thread
+
+struct ConvGemmParams {
+  const bf16* src;     // gathered operand, NHWC [Nimg, Hs, Ws, C]
+  void* dst;           // output [M, ldc] row-major (bf16 or fp32)
+  const bf16* resid;   // optional, [M, ldc] bf16, added in the epilogue
+  const float* bias;   // optional, [Ndim]
+  float* col_sum;      // optional, [Ndim] fp32: += sum over rows of the stored value
+  float* col_sqsum;    // optional, [Ndim] fp32: += sum over rows of value^2
+  int Nimg, Hs, Ws, C;
+  int Ho, Wo;
+  int KH, KW;
+  int mul, base, dk, div;  // src coord = o*mul + base + k*dk ; valid iff >=0, %div==0, /div < Hs|Ws
+  int M, Ndim, Kg;
+  int ldc;
+  int num_kb;
+  int tiles_n;
+  int out_fp32;
+  int relu;
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int A_OFF = 0;
+  static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
+  static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // +1024 alignment slack
+};
+
+// ---------------------------------------------------------------------------------------------
+// fprop / dgrad kernel
+// ---------------------------------------------------------------------------------------------
+template <int BN, int STAGES, bool A_TMA>
+__global__ void __launch_bounds__(192, 2)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                  const ConvGemmParams p) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smemA = smem + L::A_OFF;
+  uint8_t* smemB = smem + L::B_OFF;
+  uint64_t* full_bar = (uint64_t*)(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile_n = blockIdx.x % p.tiles_n;
+  const int tile_m = blockIdx.x / p.tiles_n;
+  const int m0 = tile_m * BM;
+  const int n0 = tile_n * BN;
+  const int num_kb = p.num_kb;
+
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], A_TMA ? 1u : 129u);
+      mbar_init(&empty_bar[s], 1u);
+    }
+    mbar_init(accum_bar, 1u);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmapB);
+    if (A_TMA) tma_prefetch_desc(&tmapA);
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ======================= A gather producers ==========================================
+    if (!A_TMA) {
+      const int chunk = threadIdx.x & 7;   // 16-byte chunk inside the 128-byte k-row
+      const int row0 = threadIdx.x >> 3;   // rows row0 + 16*i
+      int bh[8], bw[8];
+      int64_t ioff[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int m = m0 + row0 + 16 * i;
+        if (m < p.M) {
+          int ow = m % p.Wo;
+          int t = m / p.Wo;
+          int oh = t % p.Ho;
+          int n = t / p.Ho;
+          bh[i] = oh * p.mul + p.base;
+          bw[i] = ow * p.mul + p.base;
+          ioff[i] = (int64_t)n * p.Hs * p.Ws * p.C;
+        } else {
+          bh[i] = -(1 << 28);  // never valid
+          bw[i] = -(1 << 28);
+          ioff[i] = 0;
+        }
+      }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int k0 = kb * BK + chunk * 8;
+        const bool kvalid = k0 < p.Kg;
+        const int tap = k0 / p.C;
+        const int cc = k0 - tap * p.C;
+        const int kh = tap / p.KW;
+        const int kw = tap - kh * p.KW;
+        const int dh = kh * p.dk, dw = kw * p.dk;
+        const uint32_t stage_base = smem_u32(smemA + s * A_STAGE_BYTES);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int sh = bh[i] + dh, sw = bw[i] + dw;
+          bool v = kvalid && sh >= 0 && sw >= 0;
+          if (p.div == 2) {
+            v = v && ((sh | sw) & 1) == 0;
+            sh >>= 1;
+            sw >>= 1;
+          }
+          v = v && sh < p.Hs && sw < p.Ws;
+          const bf16* g = v ? p.src + ioff[i] + ((int64_t)sh * p.Ws + sw) * p.C + cc : p.src;
+          cp_async16_zfill(stage_base + sw128_offset(row0 + 16 * i, chunk), g, v);
+        }
+        cp_async_commit();
+        if (kb >= GATHER_LAG) {
+          cp_async_wait<GATHER_LAG>();
+          fence_proxy_async_smem();
+          mbar_arrive(&full_bar[(kb - GATHER_LAG) % STAGES]);
+        }
+      }
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      for (int kb = (num_kb > GATHER_LAG ? num_kb - GATHER_LAG : 0); kb < num_kb; ++kb)
+        mbar_arrive(&full_bar[kb % STAGES]);
+    }
+
+    // ======================= epilogue =====================================================
+    mbar_wait(accum_bar, 0);
+    tc_fence_after_sync();
+    const int row = warp * 32 + lane;
+    const int m = m0 + row;
+    const bool mvalid = m < p.M;
+    const bool do_stats = p.col_sum != nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      const int nbase = n0 + c0;
+      if (nbase >= p.Ndim) continue;  // warp-uniform
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nbase + j < p.Ndim) v[j] += __ldg(p.bias + nbase + j);
+      }
+      if (p.resid != nullptr && mvalid) {
+        const bf16* rp = p.resid + (int64_t)m * p.ldc + nbase;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (nbase + j < p.Ndim) {
+            uint4 q = *reinterpret_cast<const uint4*>(rp + j);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f = __bfloat1622float2(h[e]);
+              v[j + 2 * e] += f.x;
+              v[j + 2 * e + 1] += f.y;
+            }
+          }
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (p.out_fp32) {
+        if (mvalid) {
+          float* op = reinterpret_cast<float*>(p.dst) + (int64_t)m * p.ldc + nbase;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (nbase + j < p.Ndim)
+              *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      } else {
+        // round to bf16 first so that fused statistics describe exactly what is stored
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+        if (mvalid) {
+          bf16* op = reinterpret_cast<bf16*>(p.dst) + (int64_t)m * p.ldc + nbase;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (nbase + j < p.Ndim) {
+              uint4 q;
+              q.x = pack_bf16x2(v[j], v[j + 1]);
+              q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+              q.z = pack_bf16x2(v[j + 4], v[j + 5]);
+              q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(op + j) = q;
+            }
+          }
+        }
+      }
+      if (do_stats) {
+        // per-channel sum / sum of squares over this warp's 32 rows: butterfly transpose-reduce
+        // (31 shuffles per quantity), lane j ends up holding column j; one atomic per column per warp
+        float a[32], b[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          a[j] = mvalid ? v[j] : 0.f;
+          b[j] = a[j] * a[j];
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int j = 0; j < off; ++j) {
+            const float sa = upper ? a[j] : a[j + off];
+            const float ka = upper ? a[j + off] : a[j];
+            a[j] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
+            const float sb = upper ? b[j] : b[j + off];
+            const float kb2 = upper ? b[j + off] : b[j];
+            b[j] = kb2 + __shfl_xor_sync(0xffffffffu, sb, off);
+          }
+        }
+        if (nbase + lane < p.Ndim) {
+          atomicAdd(p.col_sum + nbase + lane, a[0]);
+          atomicAdd(p.col_sqsum + nbase + lane, b[0]);
+        }
+      }
+    }
+    tc_fence_before_sync();
+  } else if (warp == 4) {
+    // ======================= MMA issuer ===================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(1u, BM, BN, 0u, 0u);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after_sync();
+        const uint64_t adesc = make_smem_desc_sw128(smem_u32(smemA + s * A_STAGE_BYTES), 16, 1024);
+        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smemB + s * L::B_STAGE_BYTES), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                    (uint32_t)((kb | k) != 0));
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  } else {
+    // ======================= TMA producer =================================================
+    if (lane == 0) {
+      constexpr uint32_t tx = (uint32_t)L::B_STAGE_BYTES + (A_TMA ? (uint32_t)A_STAGE_BYTES : 0u);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], tx);
+        tma_load_2d(smem_u32(smemB + s * L::B_STAGE_BYTES), &tmapB, &full_bar[s], kb * BK, n0);
+        if (A_TMA) tma_load_2d(smem_u32(smemA + s * A_STAGE_BYTES), &tmapA, &full_bar[s], kb * BK, m0);
+      }
+    }
+    __syncwarp();
+  }
+
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad kernel:  dW[co, tap, ci] += sum over pixels of dY[m, co] * src[pix(m, tap), ci]
+//   A = dY  (MN-major: smem rows are pixels, 64-channel chunks along M)   via TMA
+//   B = src (MN-major: smem rows are pixels, 64-channel chunks along N)   via TMA (plain GEMM) or gather
+//   D[co 128][ci BN] accumulated in TMEM over this CTA's pixel range, then atomically added to the
+//   fp32 gradient in the reference's [Cout][Cin][KH][KW] parameter layout.
+// ---------------------------------------------------------------------------------------------
+struct WgradParams {
+  const bf16* src;   // NHWC [Nimg, Hs, Ws, C] forward input of the conv
+  float* dw;         // fp32 gradient, [Cout][Cin_real][KH][KW]
+  int Nimg, Hs, Ws, C;
+  int Ho, Wo;
+  int KH, KW;
+  int stride, pad;
+  int M;             // Nimg*Ho*Wo
+  int Cout, Cin_real;
+  int tiles_co, tiles_ci;
+  int splits, kb_per_split, num_kb_total;
+};
+
+static constexpr int WG_KROWS = 64;  // pixels per k-block
+static constexpr int WG_A_STAGE = 2 * WG_KROWS * 128;  // two 64-channel chunks (co tile = 128)
+
+template <int BN, int STAGES, bool B_TMA>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                  const WgradParams p) {
+  constexpr int NCH = BN / 64;                       // 64-channel chunks along N
+  constexpr int B_STAGE = NCH * WG_KROWS * 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smemA = smem;
+  uint8_t* smemB = smem + STAGES * WG_A_STAGE;
+  uint64_t* full_bar = (uint64_t*)(smemB + STAGES * B_STAGE);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  int bid = blockIdx.x;
+  const int tile_ci = bid % p.tiles_ci;  bid /= p.tiles_ci;
+  const int tile_co = bid % p.tiles_co;  bid /= p.tiles_co;
+  const int split = bid % p.splits;      bid /= p.splits;
+  const int tap = bid;
+  const int kh = tap / p.KW, kw = tap - kh * p.KW;
+  const int co0 = tile_co * 128;
+  const int ci0 = tile_ci * BN;
+  const int kb_begin = split * p.kb_per_split;
+  int kb_end = kb_begin + p.kb_per_split;
+  if (kb_end > p.num_kb_total) kb_end = p.num_kb_total;
+  const int nkb = kb_end - kb_begin;   // host guarantees nkb >= 1
+
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], B_TMA ? 1u : 129u);
+      mbar_init(&empty_bar[s], 1u);
+    }
+    mbar_init(accum_bar, 1u);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmapA);
+    if (B_TMA) tma_prefetch_desc(&tmapB);
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    if (!B_TMA) {
+      // gather: 64 pixel rows x (NCH*8) 16-byte chunks per stage, 128 threads
+      constexpr int CHUNKS = NCH * 8;
+      constexpr int PER_THREAD = WG_KROWS * CHUNKS / 128;
+      for (int it = 0; it < nkb; ++it) {
+        const int kb = kb_begin + it;
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const uint32_t stage_base = smem_u32(smemB + s * B_STAGE);
+#pragma unroll
+        for (int i = 0; i < PER_THREAD; ++i) {
+          const int idx = threadIdx.x + 128 * i;
+          const int chunk = idx % CHUNKS;
+          const int r = idx / CHUNKS;
+          const int m = kb * WG_KROWS + r;
+          const int ci = ci0 + chunk * 8;
+          bool v = m < p.M && ci < p.C;
+          const bf16* g = p.src;
+          if (v) {
+            int ow = m % p.Wo;
+            int t = m / p.Wo;
+            int oh = t % p.Ho;
+            int n = t / p.Ho;
+            int sh = oh * p.stride - p.pad + kh;
+            int sw = ow * p.stride - p.pad + kw;
+            v = sh >= 0 && sw >= 0 && sh < p.Hs && sw < p.Ws;
+            if (v) g = p.src + (((int64_t)n * p.Hs + sh) * p.Ws + sw) * p.C + ci;
+          }
+          const int ch64 = chunk >> 3, c16 = chunk & 7;
+          cp_async16_zfill(stage_base + ch64 * (WG_KROWS * 128) + sw128_offset(r, c16), g, v);
+        }
+        cp_async_commit();
+        if (it >= GATHER_LAG) {
+          cp_async_wait<GATHER_LAG>();
+          fence_proxy_async_smem();
+          mbar_arrive(&full_bar[(it - GATHER_LAG) % STAGES]);
+        }
+      }
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      for (int it = (nkb > GATHER_LAG ? nkb - GATHER_LAG : 0); it < nkb; ++it) mbar_arrive(&full_bar[it % STAGES]);
+    }
+    // ---------------- epilogue: TMEM -> atomicAdd into fp32 gradient ----------------------
+    mbar_wait(accum_bar, 0);
+    tc_fence_after_sync();
+    const int co = co0 + warp * 32 + lane;
+    const bool covalid = co < p.Cout;
+    const int taps = p.KH * p.KW;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      if (covalid) {
+        float* gp = p.dw + ((int64_t)co * p.Cin_real) * taps + tap;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          int ci = ci0 + c0 + j;
+          if (ci < p.Cin_real) atomicAdd(gp + (int64_t)ci * taps, __uint_as_float(r[j]));
+        }
+      }
+    }
+    tc_fence_before_sync();
+  } else if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(1u, 128, BN, 1u, 1u);  // both operands MN-major
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after_sync();
+        // MN-major SW128: LBO = stride between 64-element MN chunks, SBO = stride between 8-row K groups
+        const uint64_t adesc = make_smem_desc_sw128(smem_u32(smemA + s * WG_A_STAGE), WG_KROWS * 128, 1024);
+        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smemB + s * B_STAGE), WG_KROWS * 128, 1024);
+#pragma unroll
+        for (int k = 0; k < WG_KROWS / 16; ++k) {
+          // advance 16 pixel rows = 2048 bytes: +128 in the (addr >> 4) field
+          umma_bf16(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc,
+                    (uint32_t)((it | k) != 0));
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  } else {
+    if (lane == 0) {
+      constexpr uint32_t tx = (uint32_t)WG_A_STAGE + (B_TMA ? (uint32_t)B_STAGE : 0u);
+      for (int it = 0; it < nkb; ++it) {
+        const int kb = kb_begin + it;
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], tx);
+        const uint32_t a_base = smem_u32(smemA + s * WG_A_STAGE);
+        tma_load_2d(a_base, &tmapA, &full_bar[s], co0, kb * WG_KROWS);
+        tma_load_2d(a_base + WG_KROWS * 128, &tmapA, &full_bar[s], co0 + 64, kb * WG_KROWS);
+        if (B_TMA) {
+          const uint32_t b_base = smem_u32(smemB + s * B_STAGE);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+            tma_load_2d(b_base + c * (WG_KROWS * 128), &tmapB, &full_bar[s], ci0 + 64 * c, kb * WG_KROWS);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) {
+      set_last_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+      return nullptr;
+    }
+    fn = (PFN_encodeTiled)ptr;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: `rows` x `cols` (cols contiguous), row pitch `ld` elements, box = box_rows x 64 cols
+static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                        uint32_t box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (fn == nullptr) return -1;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(bf16)};
+  cuuint32_t box[2] = {64u, box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu ld=%llu box_rows=%u base=%p", (int)r,
+                   (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, base);
+    return -1;
+  }
+  return 0;
+}
+
+template <int BN, int STAGES, bool A_TMA>
+static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const ConvGemmParams& p, int tiles_m,
+                        cudaStream_t stream) {
+  using L = SmemLayout<BN, STAGES>;
+  auto kern = conv_igemm_kernel<BN, STAGES, A_TMA>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(conv_igemm) failed: %s", cudaGetErrorString(e));
+      return -2;
+    }
+    attr_set = true;
+  }
+  kern<<<tiles_m * p.tiles_n, 192, L::TOTAL, stream>>>(ta, tb, p);
+  return check_launch("conv_igemm_kernel");
+}
+
+}  // namespace byol
+
+using namespace byol;
+
+// out[M=Nimg*Ho*Wo, Ndim] = gather(src) x Wt^T  (+bias, +resid, relu, fused column statistics)
+// mode 0 (fprop):  src coord = o*stride - pad + k
+// mode 1 (dgrad):  src coord = (o + pad - k) / stride  (valid only when divisible); here `src` is dY,
+//                  (Hs, Ws) its spatial size and (Ho, Wo) the spatial size of dX.
+extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const void* resid, const float* bias,
+                               float* col_sum, float* col_sqsum, int Nimg, int Hs, int Ws, int C, int Ho, int Wo,
+                               int Ndim, int KH, int KW, int stride, int pad, int mode, int ldw, int ldc,
+                               int out_fp32, int relu, int force_gather, cudaStream_t stream) {
+  BYOL_CHECK_ARG(src && wt && dst, "byol_conv_igemm: null pointer");
+  BYOL_CHECK_ARG(C % 8 == 0 && C >= 8, "byol_conv_igemm: C=%d must be a multiple of 8", C);
+  BYOL_CHECK_ARG(Ndim % 8 == 0, "byol_conv_igemm: Ndim=%d must be a multiple of 8", Ndim);
+  BYOL_CHECK_ARG(ldc % 8 == 0 && ldc >= Ndim, "byol_conv_igemm: bad ldc=%d", ldc);
+  BYOL_CHECK_ARG(stride == 1 || stride == 2, "byol_conv_igemm: stride %d unsupported", stride);
+  BYOL_CHECK_ARG(mode == 0 || mode == 1, "byol_conv_igemm: bad mode %d", mode);
+  const int64_t M64 = (int64_t)Nimg * Ho * Wo;
+  BYOL_CHECK_ARG(M64 > 0 && M64 < (1ll << 31), "byol_conv_igemm: M out of range");
+  BYOL_CHECK_ARG((int64_t)Nimg * Hs * Ws * C < (1ll << 40), "byol_conv_igemm: src too large");
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.src = (const bf16*)src;
+  p.dst = dst;
+  p.resid = (const bf16*)resid;
+  p.bias = bias;
+  p.col_sum = col_sum;
+  p.col_sqsum = col_sqsum;
+  p.Nimg = Nimg; p.Hs = Hs; p.Ws = Ws; p.C = C; p.Ho = Ho; p.Wo = Wo; p.KH = KH; p.KW = KW;
+  if (mode == 0) { p.mul = stride; p.base = -pad; p.dk = 1; p.div = 1; }
+  else           { p.mul = 1; p.base = pad; p.dk = -1; p.div = stride; }
+  p.M = (int)M64;
+  p.Ndim = Ndim;
+  p.Kg = KH * KW * C;
+  BYOL_CHECK_ARG(ldw >= p.Kg && ldw % 8 == 0, "byol_conv_igemm: bad ldw=%d (Kg=%d)", ldw, p.Kg);
+  p.ldc = ldc;
+  p.num_kb = (p.Kg + BK - 1) / BK;
+  p.out_fp32 = out_fp32;
+  p.relu = relu;
+  const int BN = (Ndim > 64) ? 128 : 64;
+  p.tiles_n = (Ndim + BN - 1) / BN;
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const bool a_tma = !force_gather && KH == 1 && KW == 1 && stride == 1 && pad == 0;
+
+  CUtensorMap ta, tb;
+  memset(&ta, 0, sizeof(ta));
+  if (make_tmap_2d(&tb, wt, (uint64_t)Ndim, (uint64_t)p.Kg, (uint64_t)ldw, (uint32_t)BN) != 0) return -3;
+  if (a_tma) {
+    if (make_tmap_2d(&ta, src, (uint64_t)p.M, (uint64_t)C, (uint64_t)C, (uint32_t)BM) != 0) return -3;
+  } else {
+    ta = tb;
+  }
+  if (BN == 128) {
+    return a_tma ? launch_igemm<128, 3, true>(ta, tb, p, tiles_m, stream)
+                 : launch_igemm<128, 3, false>(ta, tb, p, tiles_m, stream);
+  }
+  return a_tma ? launch_igemm<64, 4, true>(ta, tb, p, tiles_m, stream)
+               : launch_igemm<64, 4, false>(ta, tb, p, tiles_m, stream);
+}
+
+template <int BN, bool B_TMA>
+static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, const WgradParams& p, int grid,
+                        cudaStream_t stream) {
+  constexpr int STAGES = 4;
+  constexpr int SMEM = STAGES * (WG_A_STAGE + (BN / 64) * WG_KROWS * 128) + 256 + 1024;
+  auto kern = conv_wgrad_kernel<BN, STAGES, B_TMA>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(conv_wgrad) failed: %s", cudaGetErrorString(e));
+      return -2;
+    }
+    attr_set = true;
+  }
+  kern<<<grid, 192, SMEM, stream>>>(ta, tb, p);
+  return check_launch("conv_wgrad_kernel");
+}
+
+// dW[Cout][Cin_real][KH][KW] (fp32) += dY^T x gather(src);  dy: [M, Cout] bf16, src: NHWC [Nimg,Hs,Ws,C]
+extern "C" int byol_conv_wgrad(const void* src, const void* dy, float* dw, int Nimg, int Hs, int Ws, int C,
+                               int Cin_real, int Ho, int Wo, int Cout, int KH, int KW, int stride, int pad,
+                               int force_gather, cudaStream_t stream) {
+  BYOL_CHECK_ARG(src && dy && dw, "byol_conv_wgrad: null pointer");
+  BYOL_CHECK_ARG(C % 8 == 0 && Cout % 8 == 0, "byol_conv_wgrad: C=%d, Cout=%d must be multiples of 8", C, Cout);
+  BYOL_CHECK_ARG(Cin_real <= C, "byol_conv_wgrad: Cin_real > C");
+  const int64_t M64 = (int64_t)Nimg * Ho * Wo;
+  BYOL_CHECK_ARG(M64 > 0 && M64 < (1ll << 31), "byol_conv_wgrad: M out of range");
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.src = (const bf16*)src;
+  p.dw = dw;
+  p.Nimg = Nimg; p.Hs = Hs; p.Ws = Ws; p.C = C; p.Ho = Ho; p.Wo = Wo; p.KH = KH; p.KW = KW;
+  p.stride = stride; p.pad = pad;
+  p.M = (int)M64;
+  p.Cout = Cout;
+  p.Cin_real = Cin_real;
+  const int BN = (C > 128) ? 256 : (C > 64 ? 128 : 64);
+  p.tiles_co = (Cout + 127) / 128;
+  p.tiles_ci = (C + BN - 1) / BN;
+  p.num_kb_total = (p.M + WG_KROWS - 1) / WG_KROWS;
+  const int taps = KH * KW;
+  const int base_ctas = p.tiles_co * p.tiles_ci * taps;
+  int splits = (148 * 4 + base_ctas - 1) / base_ctas;       // aim for ~4 waves of CTAs
+  int max_splits = (p.num_kb_total + 7) / 8;                // at least 8 k-blocks (512 pixels) per CTA
+  if (max_splits < 1) max_splits = 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = (p.num_kb_total + splits - 1) / splits;
+  p.splits = (p.num_kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+  const int grid = base_ctas * p.splits;
+  const bool b_tma = !force_gather && KH == 1 && KW == 1 && stride == 1 && pad == 0;
+
+  CUtensorMap ta, tb;
+  if (make_tmap_2d(&ta, dy, (uint64_t)p.M, (uint64_t)Cout, (uint64_t)Cout, (uint32_t)WG_KROWS) != 0) return -3;
+  if (b_tma) {
+    if (make_tmap_2d(&tb, src, (uint64_t)p.M, (uint64_t)C, (uint64_t)C, (uint32_t)WG_KROWS) != 0) return -3;
+  } else {
+    tb = ta;
+  }
+  switch (BN) {
+    case 256: return b_tma ? launch_wgrad<256, true>(ta, tb, p, grid, stream) : launch_wgrad<256, false>(ta, tb, p, grid, stream);
+    case 128: return b_tma ? launch_wgrad<128, true>(ta, tb, p, grid, stream) : launch_wgrad<128, false>(ta, tb, p, grid, stream);
+    default:  return b_tma ? launch_wgrad<64, true>(ta, tb, p, grid, stream) : launch_wgrad<64, false>(ta, tb, p, grid, stream);
+  }
+}

@@ -1,0 +1,293 @@
+// byol_b200 — layout conversion, weight preparation and pooling kernels (NHWC bf16 activations).
+//
+// These replace the ATen elementwise / pooling kernels under torchvision's ResNet stem and tail reached from
+// /root/reference/main.py:237 (`self.base_network(augmentation)`): MaxPool2d(3, 2, 1), AdaptiveAvgPool2d(1),
+// plus the NCHW fp32 -> NHWC bf16 input conversion and the fp32 master -> bf16 K-major weight layouts the
+// tcgen05 kernels consume.  All are HBM-bound streaming kernels: 16-byte vector accesses, grid-stride loops.
+#include "common.cuh"
+
+namespace byol {
+
+static inline int grid_for(int64_t n, int block, int max_blocks = 148 * 16) {
+  int64_t b = (n + block - 1) / block;
+  if (b > max_blocks) b = max_blocks;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// x: [N, Cin, H, W] fp32 (Cin <= 8)  ->  y: [N, H, W, 8] bf16, channels >= Cin zero
+__global__ void nchw_to_nhwc8_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t npix, int Cin,
+                                     int HW) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / HW;
+    const int hw = (int)(i - n * HW);
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = c < Cin ? __ldg(x + (n * Cin + c) * HW + hw) : 0.f;
+    uint4 q;
+    q.x = pack_bf16x2(v[0], v[1]);
+    q.y = pack_bf16x2(v[2], v[3]);
+    q.z = pack_bf16x2(v[4], v[5]);
+    q.w = pack_bf16x2(v[6], v[7]);
+    reinterpret_cast<uint4*>(y)[i] = q;
+  }
+}
+
+// w: fp32 [Cout][Cin][KH][KW]  ->  wf: bf16 [Cout][KH*KW*Cpad] (fprop, K-major)
+//                                  wd: bf16 [Cin][KH*KW*Cout]  (dgrad, K-major; optional)
+__global__ void prep_weight_kernel(const float* __restrict__ w, bf16* __restrict__ wf, bf16* __restrict__ wd,
+                                   int Cout, int Cin, int Cpad, int taps) {
+  const int64_t total = (int64_t)Cout * taps * Cpad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cpad);
+    const int64_t t = i / Cpad;
+    const int tap = (int)(t % taps);
+    const int co = (int)(t / taps);
+    float v = 0.f;
+    if (c < Cin) v = __ldg(w + ((int64_t)co * Cin + c) * taps + tap);
+    const bf16 b = __float2bfloat16_rn(v);
+    wf[i] = b;
+    if (wd != nullptr && c < Cin) wd[((int64_t)c * taps + tap) * Cout + co] = b;
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16_rn(x[i]);
+}
+
+// MaxPool (k x k, stride s, pad p) over NHWC bf16; one thread per (output pixel, 8-channel group).
+// idx (uint8, window position kh*k+kw of the first maximum in scan order) is saved for the backward pass,
+// matching ATen's max_pool2d_with_indices tie-breaking (first occurrence wins).
+__global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, uint8_t* __restrict__ idx,
+                                   int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p) {
+  const int groups = C >> 3;
+  const int64_t total = (int64_t)N * Ho * Wo * groups;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    int64_t t = i / groups;
+    const int ow = (int)(t % Wo); t /= Wo;
+    const int oh = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; bi[e] = 0; }
+    for (int kh = 0; kh < k; ++kh) {
+      const int ih = oh * s - p + kh;
+      if (ih < 0 || ih >= H) continue;
+      for (int kw = 0; kw < k; ++kw) {
+        const int iw = ow * s - p + kw;
+        if (iw < 0 || iw >= W) continue;
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)n * H + ih) * W + iw) * C + g * 8));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __bfloat1622float2(h[e]);
+          if (f.x > best[2 * e] || f.x != f.x) { best[2 * e] = f.x; bi[2 * e] = kh * k + kw; }
+          if (f.y > best[2 * e + 1] || f.y != f.y) { best[2 * e + 1] = f.y; bi[2 * e + 1] = kh * k + kw; }
+        }
+      }
+    }
+    uint4 q;
+    q.x = pack_bf16x2(best[0], best[1]);
+    q.y = pack_bf16x2(best[2], best[3]);
+    q.z = pack_bf16x2(best[4], best[5]);
+    q.w = pack_bf16x2(best[6], best[7]);
+    reinterpret_cast<uint4*>(y)[i] = q;
+    if (idx != nullptr) {
+      uint2 pk;
+      pk.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+      pk.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+      reinterpret_cast<uint2*>(idx)[i] = pk;
+    }
+  }
+}
+
+// dx[n, ih, iw, c] = sum over output windows (oh, ow) containing (ih, iw) whose saved argmax is this position
+__global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                                   bf16* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo, int k, int s,
+                                   int p) {
+  const int groups = C >> 3;
+  const int64_t total = (int64_t)N * H * W * groups;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    int64_t t = i / groups;
+    const int iw = (int)(t % W); t /= W;
+    const int ih = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int kh = 0; kh < k; ++kh) {
+      const int th = ih + p - kh;
+      if (th < 0 || th % s != 0) continue;
+      const int oh = th / s;
+      if (oh >= Ho) continue;
+      for (int kw = 0; kw < k; ++kw) {
+        const int tw = iw + p - kw;
+        if (tw < 0 || tw % s != 0) continue;
+        const int ow = tw / s;
+        if (ow >= Wo) continue;
+        const int64_t o = (((int64_t)n * Ho + oh) * Wo + ow) * groups + g;
+        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(idx) + o);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(dy) + o);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+        const int pos = kh * k + kw;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __bfloat1622float2(h[e]);
+          const uint32_t word = e < 2 ? pk.x : pk.y;
+          const int i0 = (word >> (16 * (e & 1))) & 0xff;
+          const int i1 = (word >> (16 * (e & 1) + 8)) & 0xff;
+          if (i0 == pos) acc[2 * e] += f.x;
+          if (i1 == pos) acc[2 * e + 1] += f.y;
+        }
+      }
+    }
+    uint4 q;
+    q.x = pack_bf16x2(acc[0], acc[1]);
+    q.y = pack_bf16x2(acc[2], acc[3]);
+    q.z = pack_bf16x2(acc[4], acc[5]);
+    q.w = pack_bf16x2(acc[6], acc[7]);
+    reinterpret_cast<uint4*>(dx)[i] = q;
+  }
+}
+
+// global average pool: x [N, HW, C] bf16 -> y_f32 [N, C] fp32 and y_bf16 [N, C] (both optional)
+__global__ void avgpool_fwd_kernel(const bf16* __restrict__ x, float* __restrict__ y_f32, bf16* __restrict__ y_bf16,
+                                   int N, int HW, int C) {
+  const int groups = C >> 3;
+  const int64_t total = (int64_t)N * groups;
+  const float inv = 1.f / (float)HW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const int64_t n = i / groups;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int r = 0; r < HW; ++r) {
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(x + ((int64_t)n * HW + r) * C + g * 8));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __bfloat1622float2(h[e]);
+        acc[2 * e] += f.x;
+        acc[2 * e + 1] += f.y;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= inv;
+    if (y_f32 != nullptr) {
+      float4* o = reinterpret_cast<float4*>(y_f32 + n * C + g * 8);
+      o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    if (y_bf16 != nullptr) {
+      uint4 q;
+      q.x = pack_bf16x2(acc[0], acc[1]);
+      q.y = pack_bf16x2(acc[2], acc[3]);
+      q.z = pack_bf16x2(acc[4], acc[5]);
+      q.w = pack_bf16x2(acc[6], acc[7]);
+      *reinterpret_cast<uint4*>(y_bf16 + n * C + g * 8) = q;
+    }
+  }
+}
+
+// dx[n, r, c] = (g_a[n, c] (+ g_b[n, c])) / HW     (g_a bf16 from dgrad, g_b fp32 from autograd; either may be null)
+__global__ void avgpool_bwd_kernel(const bf16* __restrict__ g_a, const float* __restrict__ g_b,
+                                   bf16* __restrict__ dx, int N, int HW, int C) {
+  const int groups = C >> 3;
+  const int64_t total = (int64_t)N * HW * groups;
+  const float inv = 1.f / (float)HW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const int64_t n = i / ((int64_t)HW * groups);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (g_a != nullptr) {
+      uint4 q = __ldg(reinterpret_cast<const uint4*>(g_a + n * C + g * 8));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __bfloat1622float2(h[e]);
+        v[2 * e] += f.x;
+        v[2 * e + 1] += f.y;
+      }
+    }
+    if (g_b != nullptr) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += __ldg(g_b + n * C + g * 8 + e);
+    }
+    uint4 q;
+    q.x = pack_bf16x2(v[0] * inv, v[1] * inv);
+    q.y = pack_bf16x2(v[2] * inv, v[3] * inv);
+    q.z = pack_bf16x2(v[4] * inv, v[5] * inv);
+    q.w = pack_bf16x2(v[6] * inv, v[7] * inv);
+    reinterpret_cast<uint4*>(dx)[i] = q;
+  }
+}
+
+}  // namespace byol
+
+using namespace byol;
+
+extern "C" int byol_nchw_to_nhwc8(const float* x, void* y, int N, int Cin, int H, int W, cudaStream_t stream) {
+  BYOL_CHECK_ARG(x && y && N > 0 && Cin > 0 && Cin <= 8 && H > 0 && W > 0, "byol_nchw_to_nhwc8: bad args");
+  const int64_t npix = (int64_t)N * H * W;
+  nchw_to_nhwc8_kernel<<<grid_for(npix, 256), 256, 0, stream>>>(x, (bf16*)y, npix, Cin, H * W);
+  return check_launch("nchw_to_nhwc8_kernel");
+}
+
+extern "C" int byol_prep_weight(const float* w, void* w_fprop, void* w_dgrad, int Cout, int Cin, int Cpad, int KH,
+                                int KW, cudaStream_t stream) {
+  BYOL_CHECK_ARG(w && w_fprop && Cout > 0 && Cin > 0 && Cpad >= Cin && Cpad % 8 == 0, "byol_prep_weight: bad args");
+  BYOL_CHECK_ARG(w_dgrad == nullptr || Cout % 8 == 0, "byol_prep_weight: dgrad layout needs Cout %% 8 == 0");
+  const int64_t total = (int64_t)Cout * KH * KW * Cpad;
+  prep_weight_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, (bf16*)w_fprop, (bf16*)w_dgrad, Cout, Cin, Cpad,
+                                                              KH * KW);
+  return check_launch("prep_weight_kernel");
+}
+
+extern "C" int byol_cast_f32_bf16(const float* x, void* y, int64_t n, cudaStream_t stream) {
+  BYOL_CHECK_ARG(x && y && n > 0, "byol_cast_f32_bf16: bad args");
+  cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, (bf16*)y, n);
+  return check_launch("cast_f32_bf16_kernel");
+}
+
+extern "C" int byol_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, int k, int s, int p,
+                                cudaStream_t stream) {
+  BYOL_CHECK_ARG(x && y && C % 8 == 0 && k * k <= 255, "byol_maxpool_fwd: bad args");
+  const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
+  const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+  maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const bf16*)x, (bf16*)y, (uint8_t*)idx, N, H, W, C,
+                                                              Ho, Wo, k, s, p);
+  return check_launch("maxpool_fwd_kernel");
+}
+
+extern "C" int byol_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, int k, int s,
+                                int p, cudaStream_t stream) {
+  BYOL_CHECK_ARG(dy && idx && dx && C % 8 == 0, "byol_maxpool_bwd: bad args");
+  const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
+  const int64_t total = (int64_t)N * H * W * (C / 8);
+  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const bf16*)dy, (const uint8_t*)idx, (bf16*)dx, N, H,
+                                                              W, C, Ho, Wo, k, s, p);
+  return check_launch("maxpool_bwd_kernel");
+}
+
+extern "C" int byol_avgpool_fwd(const void* x, float* y_f32, void* y_bf16, int N, int HW, int C,
+                                cudaStream_t stream) {
+  BYOL_CHECK_ARG(x && (y_f32 || y_bf16) && C % 8 == 0 && HW > 0, "byol_avgpool_fwd: bad args");
+  avgpool_fwd_kernel<<<grid_for((int64_t)N * (C / 8), 128), 128, 0, stream>>>((const bf16*)x, y_f32, (bf16*)y_bf16,
+                                                                              N, HW, C);
+  return check_launch("avgpool_fwd_kernel");
+}
+
+extern "C" int byol_avgpool_bwd(const void* g_bf16, const float* g_f32, void* dx, int N, int HW, int C,
+                                cudaStream_t stream) {
+  BYOL_CHECK_ARG((g_bf16 || g_f32) && dx && C % 8 == 0 && HW > 0, "byol_avgpool_bwd: bad args");
+  avgpool_bwd_kernel<<<grid_for((int64_t)N * HW * (C / 8), 256), 256, 0, stream>>>((const bf16*)g_bf16, g_f32,
+                                                                                    (bf16*)dx, N, HW, C);
+  return check_launch("avgpool_bwd_kernel");
+}

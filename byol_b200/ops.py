@@ -1,0 +1,289 @@
+"""Thin Python wrappers over the C-ABI kernels (``include/byol_b200.h``).
+
+PyTorch is used only as the owner of device memory and of the CUDA stream: every function borrows
+``tensor.data_ptr()`` for the duration of one asynchronous launch on ``torch.cuda.current_stream()``.
+There is no CPU / ATen fallback; calling any of these without the CUDA extension raises at import time.
+
+Layout conventions: activations NHWC bf16 with channels padded to a multiple of 8; weights for the
+tensor-core kernels bf16 ``[Cout, KH*KW*Cpad]`` (fprop) / ``[Cin, KH*KW*Cout]`` (dgrad) made by
+:func:`prep_weight` from the fp32 master in the reference's ``[Cout, Cin, KH, KW]`` layout.
+"""
+import torch
+
+from ._lib import lib, check
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor (byol_b200 has no CPU path)" % name)
+    if t.dtype != dtype:
+        raise ValueError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+
+
+def conv_out_size(h, k, s, p):
+    return (h + 2 * p - k) // s + 1
+
+
+# ------------------------------------------------------------------------------------------------
+# layout / weights
+# ------------------------------------------------------------------------------------------------
+def nchw_to_nhwc8(x, out=None):
+    """fp32 NCHW [N, C<=8, H, W] -> bf16 NHWC [N, H, W, 8] (zero padded channels)."""
+    _chk(x, F32, "x")
+    n, c, h, w = x.shape
+    if out is None:
+        out = torch.empty((n, h, w, 8), dtype=BF16, device=x.device)
+    check(lib.byol_nchw_to_nhwc8(_ptr(x), _ptr(out), n, c, h, w, _stream()), "byol_nchw_to_nhwc8")
+    return out
+
+
+def prep_weight(w, cpad=None, want_dgrad=True, out_f=None, out_d=None):
+    """fp32 [Cout, Cin, KH, KW] (or [out, in] for Linear) -> (w_fprop bf16 [Cout, taps*Cpad], w_dgrad bf16 [Cin, taps*Cout])."""
+    _chk(w, F32, "w")
+    if w.dim() == 2:
+        cout, cin = w.shape
+        kh = kw = 1
+    else:
+        cout, cin, kh, kw = w.shape
+    if cpad is None:
+        cpad = (cin + 7) // 8 * 8
+    if out_f is None:
+        out_f = torch.empty((cout, kh * kw * cpad), dtype=BF16, device=w.device)
+    if want_dgrad and out_d is None:
+        out_d = torch.empty((cin, kh * kw * cout), dtype=BF16, device=w.device)
+    check(lib.byol_prep_weight(_ptr(w), _ptr(out_f), _ptr(out_d) if want_dgrad else 0, cout, cin, cpad, kh, kw,
+                               _stream()), "byol_prep_weight")
+    return out_f, (out_d if want_dgrad else None)
+
+
+def cast_bf16(x, out=None):
+    _chk(x, F32, "x")
+    if out is None:
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    check(lib.byol_cast_f32_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "byol_cast_f32_bf16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core convolution / linear
+# ------------------------------------------------------------------------------------------------
+def conv_fprop(x, w_f, kh, kw, stride, pad, bias=None, resid=None, stats=None, relu=False, out_fp32=False,
+               out=None, force_gather=False):
+    """y[N,Ho,Wo,Cout] = conv(x[N,H,W,C], w).  stats: optional zeroed fp32 [2*Cout] receiving column sum / sqsum."""
+    _chk(x, BF16, "x"); _chk(w_f, BF16, "w_f"); _chk(bias, F32, "bias"); _chk(resid, BF16, "resid")
+    _chk(stats, F32, "stats")
+    n, h, w, c = x.shape
+    cout, ldw = w_f.shape
+    ho, wo = conv_out_size(h, kh, stride, pad), conv_out_size(w, kw, stride, pad)
+    if out is None:
+        out = torch.empty((n, ho, wo, cout), dtype=F32 if out_fp32 else BF16, device=x.device)
+    cs = _ptr(stats)
+    cq = (stats.data_ptr() + 4 * cout) if stats is not None else 0
+    check(lib.byol_conv_igemm(_ptr(x), _ptr(w_f), _ptr(out), _ptr(resid), _ptr(bias), cs, cq, n, h, w, c, ho, wo,
+                              cout, kh, kw, stride, pad, 0, ldw, cout, int(out_fp32), int(relu), int(force_gather),
+                              _stream()), "byol_conv_igemm(fprop)")
+    return out
+
+
+def conv_dgrad(dy, w_d, h, w, kh, kw, stride, pad, resid=None, out=None, force_gather=False):
+    """dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], w);  w_d is the dgrad layout [Cin, taps*Cout]."""
+    _chk(dy, BF16, "dy"); _chk(w_d, BF16, "w_d"); _chk(resid, BF16, "resid")
+    n, ho, wo, cout = dy.shape
+    cin, ldw = w_d.shape
+    if out is None:
+        out = torch.empty((n, h, w, cin), dtype=BF16, device=dy.device)
+    check(lib.byol_conv_igemm(_ptr(dy), _ptr(w_d), _ptr(out), _ptr(resid), 0, 0, 0, n, ho, wo, cout, h, w, cin,
+                              kh, kw, stride, pad, 1, ldw, cin, 0, 0, int(force_gather), _stream()),
+          "byol_conv_igemm(dgrad)")
+    return out
+
+
+def conv_wgrad(x, dy, dw, kh, kw, stride, pad, force_gather=False):
+    """dw[Cout,Cin,KH,KW] (fp32, reference layout) += dy^T * im2col(x).  x: [N,H,W,Cpad], dy: [N,Ho,Wo,Cout]."""
+    _chk(x, BF16, "x"); _chk(dy, BF16, "dy"); _chk(dw, F32, "dw")
+    n, h, w, c = x.shape
+    _, ho, wo, cout = dy.shape
+    cin_real = dw.shape[1]
+    check(lib.byol_conv_wgrad(_ptr(x), _ptr(dy), _ptr(dw), n, h, w, c, cin_real, ho, wo, cout, kh, kw, stride, pad,
+                              int(force_gather), _stream()), "byol_conv_wgrad")
+    return dw
+
+
+def linear_fprop(x2d, w_f, bias=None, stats=None, relu=False, out_fp32=False, out=None):
+    """y[M, out] = x[M, in] @ W^T (+bias): a 1x1 'convolution' over M pixels."""
+    m, k = x2d.shape
+    y = conv_fprop(x2d.view(m, 1, 1, k), w_f, 1, 1, 1, 0, bias=bias, stats=stats, relu=relu, out_fp32=out_fp32,
+                   out=None if out is None else out.view(m, 1, 1, -1))
+    return y.view(m, -1)
+
+
+def linear_dgrad(dy2d, w_d, out=None):
+    m, n = dy2d.shape
+    dx = conv_dgrad(dy2d.view(m, 1, 1, n), w_d, 1, 1, 1, 1, 1, 0, out=None if out is None else out.view(m, 1, 1, -1))
+    return dx.view(m, -1)
+
+
+def linear_wgrad(x2d, dy2d, dw):
+    m, k = x2d.shape
+    n = dy2d.shape[1]
+    conv_wgrad(x2d.view(m, 1, 1, k), dy2d.view(m, 1, 1, n), dw.view(n, dw.shape[1], 1, 1), 1, 1, 1, 0)
+    return dw
+
+
+# ------------------------------------------------------------------------------------------------
+# batch norm
+# ------------------------------------------------------------------------------------------------
+def bn_stats(x2d, stats):
+    """stats (zeroed fp32 [2C]) += [column sums, column sums of squares] of x2d [M, C] bf16."""
+    _chk(x2d, BF16, "x"); _chk(stats, F32, "stats")
+    m, c = x2d.shape
+    check(lib.byol_bn_stats(_ptr(x2d), _ptr(stats), m, c, _stream()), "byol_bn_stats")
+    return stats
+
+
+def bn_finalize(stats, count, gamma, beta, running_mean, running_var, momentum, eps, coeffs):
+    """coeffs: fp32 [4, C] receiving scale, shift, mean, invstd.  running_* updated in place (may be None)."""
+    c = gamma.numel()
+    check(lib.byol_bn_finalize(_ptr(stats), float(count), _ptr(gamma), _ptr(beta), _ptr(running_mean),
+                               _ptr(running_var), float(momentum), float(eps), _ptr(coeffs[0]), _ptr(coeffs[1]),
+                               _ptr(coeffs[2]), _ptr(coeffs[3]), c, _stream()), "byol_bn_finalize")
+    return coeffs
+
+
+def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, coeffs):
+    c = gamma.numel()
+    check(lib.byol_bn_eval_coeffs(_ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), float(eps),
+                                  _ptr(coeffs[0]), _ptr(coeffs[1]), c, _stream()), "byol_bn_eval_coeffs")
+    return coeffs
+
+
+def bn_apply(x2d, scale, shift, relu, resid=None, rscale=None, rshift=None, out=None, out_f32=None):
+    _chk(x2d, BF16, "x"); _chk(resid, BF16, "resid")
+    m, c = x2d.shape
+    if out is None and out_f32 is None:
+        out = torch.empty_like(x2d)
+    check(lib.byol_bn_apply(_ptr(x2d), _ptr(scale), _ptr(shift), _ptr(resid), _ptr(rscale), _ptr(rshift), _ptr(out),
+                            _ptr(out_f32), m, c, int(relu), _stream()), "byol_bn_apply")
+    return out if out is not None else out_f32
+
+
+def bn_bwd_reduce(g, x, coeffs, s12, mask_mode, act=None):
+    """s12 (zeroed fp32 [2C]) += [sum dz, sum dz*xhat];  mask_mode 0 none / 1 relu(x*scale+shift) / 2 act>0."""
+    _chk(g, BF16, "g"); _chk(x, BF16, "x"); _chk(act, BF16, "act")
+    m, c = x.shape
+    check(lib.byol_bn_bwd_reduce(_ptr(g), _ptr(x), _ptr(act), _ptr(coeffs[0]), _ptr(coeffs[1]), _ptr(coeffs[2]),
+                                 _ptr(coeffs[3]), _ptr(s12), m, c, mask_mode, _stream()), "byol_bn_bwd_reduce")
+    return s12
+
+
+def bn_bwd_apply(g, x, coeffs, gamma, s12, count, mask_mode, act=None, dy=None, dz_out=None):
+    _chk(g, BF16, "g"); _chk(x, BF16, "x"); _chk(act, BF16, "act")
+    m, c = x.shape
+    if dy is None:
+        dy = torch.empty_like(x)
+    check(lib.byol_bn_bwd_apply(_ptr(g), _ptr(x), _ptr(act), _ptr(coeffs[0]), _ptr(coeffs[1]), _ptr(coeffs[2]),
+                                _ptr(coeffs[3]), _ptr(gamma), _ptr(s12), float(count), _ptr(dy), _ptr(dz_out), m, c,
+                                mask_mode, _stream()), "byol_bn_bwd_apply")
+    return dy
+
+
+def col_sum(x2d, out):
+    """out[c] (fp32) += sum_r x2d[r, c]."""
+    m, c = x2d.shape
+    check(lib.byol_col_sum(_ptr(x2d), _ptr(out), m, c, x2d.stride(0), int(x2d.dtype == F32), _stream()),
+          "byol_col_sum")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# pooling
+# ------------------------------------------------------------------------------------------------
+def maxpool_fwd(x, k=3, s=2, p=1, want_idx=True):
+    _chk(x, BF16, "x")
+    n, h, w, c = x.shape
+    ho, wo = conv_out_size(h, k, s, p), conv_out_size(w, k, s, p)
+    y = torch.empty((n, ho, wo, c), dtype=BF16, device=x.device)
+    idx = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=x.device) if want_idx else None
+    check(lib.byol_maxpool_fwd(_ptr(x), _ptr(y), _ptr(idx), n, h, w, c, k, s, p, _stream()), "byol_maxpool_fwd")
+    return y, idx
+
+
+def maxpool_bwd(dy, idx, h, w, k=3, s=2, p=1):
+    _chk(dy, BF16, "dy")
+    n, ho, wo, c = dy.shape
+    dx = torch.empty((n, h, w, c), dtype=BF16, device=dy.device)
+    check(lib.byol_maxpool_bwd(_ptr(dy), _ptr(idx), _ptr(dx), n, h, w, c, k, s, p, _stream()), "byol_maxpool_bwd")
+    return dx
+
+
+def avgpool_fwd(x, want_f32=True, want_bf16=True):
+    _chk(x, BF16, "x")
+    n, h, w, c = x.shape
+    yf = torch.empty((n, c), dtype=F32, device=x.device) if want_f32 else None
+    yb = torch.empty((n, c), dtype=BF16, device=x.device) if want_bf16 else None
+    check(lib.byol_avgpool_fwd(_ptr(x), _ptr(yf), _ptr(yb), n, h * w, c, _stream()), "byol_avgpool_fwd")
+    return yf, yb
+
+
+def avgpool_bwd(g_bf16, g_f32, n, h, w, c):
+    _chk(g_bf16, BF16, "g_bf16"); _chk(g_f32, F32, "g_f32")
+    dev = (g_bf16 if g_bf16 is not None else g_f32).device
+    dx = torch.empty((n, h, w, c), dtype=BF16, device=dev)
+    check(lib.byol_avgpool_bwd(_ptr(g_bf16), _ptr(g_f32), _ptr(dx), n, h * w, c, _stream()), "byol_avgpool_bwd")
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# objective / EMA / LARS
+# ------------------------------------------------------------------------------------------------
+def loss_fwd(q1, q2, z1, z2, workspace, loss, saved):
+    for t, nm in ((q1, "q1"), (q2, "q2"), (z1, "z1"), (z2, "z2")):
+        _chk(t, F32, nm)
+    rows, dim = q1.shape
+    check(lib.byol_loss_fwd(_ptr(q1), _ptr(q2), _ptr(z1), _ptr(z2), rows, dim, _ptr(workspace), _ptr(loss),
+                            _ptr(saved), _stream()), "byol_loss_fwd")
+    return loss
+
+
+def loss_bwd(q1, q2, z1, z2, saved, grad_out, dq1, dq2):
+    rows, dim = q1.shape
+    check(lib.byol_loss_bwd(_ptr(q1), _ptr(q2), _ptr(z1), _ptr(z2), _ptr(saved), _ptr(grad_out), _ptr(dq1),
+                            _ptr(dq2), rows, dim, _stream()), "byol_loss_bwd")
+    return dq1, dq2
+
+
+def ema_update(x, mean, one_minus_decay, decay):
+    """mean <- fl(fl(a*x) + fl(d*mean)) in place; a, d already rounded to fp32 by the caller."""
+    _chk(x, F32, "x"); _chk(mean, F32, "mean")
+    if x.numel() != mean.numel():
+        raise ValueError("ema_update: size mismatch")
+    check(lib.byol_ema_update(_ptr(x), _ptr(mean), float(one_minus_decay), float(decay), x.numel(), _stream()),
+          "byol_ema_update")
+    return mean
+
+
+def lars_sgd_step(params, grads, mom, table, trust_coef, eps, momentum, first_step):
+    """table: dict with device tensors chunk_start(int64), chunk_len(int32), chunk_tensor(int32), wd, lr (fp32),
+    ignore (int32), norms (fp64 [2*T])."""
+    _chk(params, F32, "params"); _chk(grads, F32, "grads"); _chk(mom, F32, "mom")
+    check(lib.byol_lars_sgd_step(_ptr(params), _ptr(grads), _ptr(mom), _ptr(table["chunk_start"]),
+                                 _ptr(table["chunk_len"]), _ptr(table["chunk_tensor"]),
+                                 table["chunk_start"].numel(), _ptr(table["wd"]), _ptr(table["lr"]),
+                                 _ptr(table["ignore"]), table["wd"].numel(), _ptr(table["norms"]),
+                                 float(trust_coef), float(eps), float(momentum), int(first_step), _stream()),
+          "byol_lars_sgd_step")

@@ -1,0 +1,138 @@
+"""GPU parity: tcgen05 implicit-GEMM conv / linear (fprop, dgrad, wgrad) vs the CPU oracle (oracle/ops_ref.py).
+
+Inputs are bf16-representable, the oracle runs in fp32 on the same values, so the only differences are fp32
+accumulation order (tolerance 2e-3 relative to the output scale, stated per test) and, where the kernel
+stores bf16, one bf16 rounding (2^-8 relative).
+"""
+import pytest
+import torch
+
+from oracle import ops_ref as R
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+# (name, N, H, W, Cin_real, Cpad, Cout, k, stride, pad)
+CONV_CASES = [
+    ("1x1_64_64", 2, 8, 8, 64, 64, 64, 1, 1, 0),
+    ("1x1_256_128", 2, 8, 8, 256, 256, 128, 1, 1, 0),
+    ("1x1_64_256", 2, 8, 8, 64, 64, 256, 1, 1, 0),
+    ("1x1_tailM", 3, 7, 7, 128, 128, 64, 1, 1, 0),
+    ("3x3_64_64", 2, 8, 8, 64, 64, 64, 3, 1, 1),
+    ("3x3_128_128", 2, 14, 14, 128, 128, 128, 3, 1, 1),
+    ("3x3s2_128_128", 1, 28, 28, 128, 128, 128, 3, 2, 1),
+    ("1x1s2_256_512", 1, 28, 28, 256, 256, 512, 1, 2, 0),
+    ("3x3_512_512_7", 3, 7, 7, 512, 512, 512, 3, 1, 1),
+    ("stem7x7", 2, 32, 32, 3, 8, 64, 7, 2, 3),
+]
+
+
+def _mk(case, dev, seed=0):
+    name, n, h, w, cin, cpad, cout, k, s, p = case
+    g = torch.Generator().manual_seed(seed)
+    x = R.bf16_round(torch.randn(n, h, w, cin, generator=g))
+    wt = R.bf16_round(torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5)
+    xp = torch.zeros(n, h, w, cpad)
+    xp[..., :cin] = x
+    return x, wt, xp.to(dev, torch.bfloat16)
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+@pytest.mark.parametrize("force_gather", [False, True], ids=["auto", "gather"])
+def test_conv_fprop(cuda, case, force_gather):
+    from byol_b200 import ops
+    name, n, h, w, cin, cpad, cout, k, s, p = case
+    x, wt, xd = _mk(case, cuda)
+    w_f, _ = ops.prep_weight(wt.to(cuda), cpad=cpad, want_dgrad=False)
+    ref = R.conv_fprop_ref(x, wt, s, p)
+    y32 = ops.conv_fprop(xd, w_f, k, k, s, p, out_fp32=True, force_gather=force_gather)
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    assert_close("fprop_f32[%s]" % name, y32, ref, atol=2e-3 * scale, rtol=0)
+    stats = torch.zeros(2 * cout, device=cuda)
+    y16 = ops.conv_fprop(xd, w_f, k, k, s, p, stats=stats, force_gather=force_gather)
+    torch.cuda.synchronize()
+    assert_close("fprop_bf16[%s]" % name, y16, ref, atol=1e-2 * scale, rtol=0)
+    yr = y16.float().cpu().reshape(-1, cout)
+    assert_close("fprop_stats_sum[%s]" % name, stats[:cout], yr.sum(0), atol=1e-3 * yr.abs().sum(0).max().item(), rtol=0)
+    assert_close("fprop_stats_sq[%s]" % name, stats[cout:], (yr * yr).sum(0), atol=0, rtol=1e-3)
+
+
+def test_conv_fprop_epilogue(cuda):
+    from byol_b200 import ops
+    case = ("3x3_64_64", 2, 8, 8, 64, 64, 64, 3, 1, 1)
+    name, n, h, w, cin, cpad, cout, k, s, p = case
+    x, wt, xd = _mk(case, cuda, seed=3)
+    g = torch.Generator().manual_seed(5)
+    bias = torch.randn(cout, generator=g)
+    resid = R.bf16_round(torch.randn(n, h, w, cout, generator=g))
+    w_f, _ = ops.prep_weight(wt.to(cuda), cpad=cpad, want_dgrad=False)
+    ref = R.conv_fprop_ref(x, wt, s, p, bias=bias, resid_nhwc=resid, relu=True)
+    y = ops.conv_fprop(xd, w_f, k, k, s, p, bias=bias.to(cuda), resid=resid.to(cuda, torch.bfloat16), relu=True,
+                       out_fp32=True)
+    torch.cuda.synchronize()
+    assert_close("fprop_epilogue", y, ref, atol=2e-3 * float(ref.abs().max()), rtol=0)
+
+
+@pytest.mark.parametrize("case", CONV_CASES[:-1], ids=[c[0] for c in CONV_CASES[:-1]])
+@pytest.mark.parametrize("force_gather", [False, True], ids=["auto", "gather"])
+def test_conv_dgrad(cuda, case, force_gather):
+    from byol_b200 import ops
+    name, n, h, w, cin, cpad, cout, k, s, p = case
+    _, wt, _ = _mk(case, cuda)
+    ho, wo = ops.conv_out_size(h, k, s, p), ops.conv_out_size(w, k, s, p)
+    g = torch.Generator().manual_seed(11)
+    dy = R.bf16_round(torch.randn(n, ho, wo, cout, generator=g))
+    _, w_d = ops.prep_weight(wt.to(cuda), cpad=cpad, want_dgrad=True)
+    ref = R.conv_dgrad_ref(dy, wt, (h, w), s, p)
+    dx = ops.conv_dgrad(dy.to(cuda, torch.bfloat16), w_d, h, w, k, k, s, p, force_gather=force_gather)
+    torch.cuda.synchronize()
+    assert_close("dgrad[%s]" % name, dx, ref, atol=1e-2 * float(ref.abs().max()), rtol=0)
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+@pytest.mark.parametrize("force_gather", [False, True], ids=["auto", "gather"])
+def test_conv_wgrad(cuda, case, force_gather):
+    from byol_b200 import ops
+    name, n, h, w, cin, cpad, cout, k, s, p = case
+    x, wt, xd = _mk(case, cuda)
+    ho, wo = ops.conv_out_size(h, k, s, p), ops.conv_out_size(w, k, s, p)
+    g = torch.Generator().manual_seed(13)
+    dy = R.bf16_round(torch.randn(n, ho, wo, cout, generator=g))
+    ref = R.conv_wgrad_ref(x, dy, wt.shape, s, p)
+    dw = torch.zeros(cout, cin, k, k, device=cuda)
+    ops.conv_wgrad(xd, dy.to(cuda, torch.bfloat16), dw, k, k, s, p, force_gather=force_gather)
+    torch.cuda.synchronize()
+    assert_close("wgrad[%s]" % name, dw, ref, atol=2e-3 * float(ref.abs().max()), rtol=0)
+    # accumulate semantics: a second call doubles the result
+    ops.conv_wgrad(xd, dy.to(cuda, torch.bfloat16), dw, k, k, s, p, force_gather=force_gather)
+    torch.cuda.synchronize()
+    assert_close("wgrad_acc[%s]" % name, dw, 2 * ref, atol=4e-3 * float(ref.abs().max()), rtol=0)
+
+
+LINEAR_CASES = [("head1", 64, 2048, 4096), ("head2", 64, 4096, 256), ("cls", 96, 2048, 1000), ("pred1", 200, 256, 4096)]
+
+
+@pytest.mark.parametrize("case", LINEAR_CASES, ids=[c[0] for c in LINEAR_CASES])
+def test_linear(cuda, case):
+    from byol_b200 import ops
+    name, m, k, n = case
+    g = torch.Generator().manual_seed(17)
+    x = R.bf16_round(torch.randn(m, k, generator=g))
+    w = R.bf16_round(torch.randn(n, k, generator=g) / k ** 0.5)
+    b = torch.randn(n, generator=g)
+    dy = R.bf16_round(torch.randn(m, n, generator=g))
+    w_f, w_d = ops.prep_weight(w.to(cuda), want_dgrad=(n % 8 == 0))
+    y = ops.linear_fprop(x.to(cuda, torch.bfloat16), w_f, bias=b.to(cuda), out_fp32=True)
+    torch.cuda.synchronize()
+    ref = x @ w.t() + b
+    assert_close("linear_fprop[%s]" % name, y, ref, atol=2e-3 * float(ref.abs().max()), rtol=0)
+    dx = ops.linear_dgrad(dy.to(cuda, torch.bfloat16), w_d)
+    torch.cuda.synchronize()
+    refdx = dy @ w
+    assert_close("linear_dgrad[%s]" % name, dx, refdx, atol=1e-2 * float(refdx.abs().max()), rtol=0)
+    dw = torch.zeros(n, k, device=cuda)
+    ops.linear_wgrad(x.to(cuda, torch.bfloat16), dy.to(cuda, torch.bfloat16), dw)
+    torch.cuda.synchronize()
+    refdw = dy.t() @ x
+    assert_close("linear_wgrad[%s]" % name, dw, refdw, atol=2e-3 * float(refdw.abs().max()), rtol=0)

@@ -1,0 +1,235 @@
+"""GPU parity for the HBM-bound kernels: BN fwd/bwd, pooling, layout, loss, EMA (bit-exact), LARS+SGD."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops_ref as R
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+@pytest.mark.parametrize("m,c", [(300, 64), (128, 256), (70, 4096), (1000, 8)])
+def test_bn_forward(cuda, m, c):
+    from byol_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    x = R.bf16_round(torch.randn(m, c, generator=g) * 2 + 0.5)
+    gamma = torch.rand(c, generator=g) + 0.5
+    beta = torch.randn(c, generator=g)
+    rm, rv = torch.zeros(c), torch.ones(c)
+    xd = x.to(cuda, BF)
+    stats = torch.zeros(2 * c, device=cuda)
+    ops.bn_stats(xd, stats)
+    coeffs = torch.empty(4, c, device=cuda)
+    rmd, rvd = rm.to(cuda), rv.to(cuda)
+    ops.bn_finalize(stats, m, gamma.to(cuda), beta.to(cuda), rmd, rvd, 0.1, 1e-5, coeffs)
+    y = ops.bn_apply(xd, coeffs[0], coeffs[1], relu=True)
+    torch.cuda.synchronize()
+    yref, mean, invstd, var = R.bn_train_ref(x, gamma, beta)
+    assert_close("bn_mean", coeffs[2], mean, atol=1e-5, rtol=1e-5)
+    assert_close("bn_invstd", coeffs[3], invstd, atol=0, rtol=1e-4)
+    assert_close("bn_apply_relu", y, torch.relu(yref), atol=2e-2, rtol=1e-2)
+    assert_close("bn_running_mean", rmd, 0.9 * rm + 0.1 * mean, atol=1e-5, rtol=1e-5)
+    assert_close("bn_running_var", rvd, 0.9 * rv + 0.1 * var * m / (m - 1), atol=1e-5, rtol=1e-4)
+
+
+def test_bn_apply_residual(cuda):
+    from byol_b200 import ops
+    m, c = 200, 128
+    g = torch.Generator().manual_seed(2)
+    x = R.bf16_round(torch.randn(m, c, generator=g))
+    r = R.bf16_round(torch.randn(m, c, generator=g))
+    sc, sh, rs, rsh = [torch.randn(c, generator=g) for _ in range(4)]
+    y1 = ops.bn_apply(x.to(cuda, BF), sc.to(cuda), sh.to(cuda), relu=True, resid=r.to(cuda, BF))
+    y2 = ops.bn_apply(x.to(cuda, BF), sc.to(cuda), sh.to(cuda), relu=True, resid=r.to(cuda, BF), rscale=rs.to(cuda),
+                      rshift=rsh.to(cuda))
+    torch.cuda.synchronize()
+    assert_close("bn_apply_resid", y1, torch.relu(x * sc + sh + r), atol=3e-2, rtol=1e-2)
+    assert_close("bn_apply_resid_affine", y2, torch.relu(x * sc + sh + r * rs + rsh), atol=3e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize("mask_mode", [0, 1, 2])
+@pytest.mark.parametrize("m,c", [(300, 64), (96, 4096)])
+def test_bn_backward(cuda, mask_mode, m, c):
+    from byol_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = R.bf16_round(torch.randn(m, c, generator=g) + 0.3)
+    gy = R.bf16_round(torch.randn(m, c, generator=g))
+    gamma = torch.rand(c, generator=g) + 0.5
+    beta = torch.randn(c, generator=g) * 0.1
+    yref, mean, invstd, var = R.bn_train_ref(x, gamma, beta)
+    scale = gamma * invstd
+    shift = beta - mean * scale
+    coeffs = torch.stack([scale, shift, mean, invstd]).to(cuda)
+    act = None
+    if mask_mode == 0:
+        dz = gy
+    elif mask_mode == 1:
+        dz = gy * ((x * scale + shift) > 0)
+    else:
+        act = R.bf16_round(torch.relu(yref + torch.randn(m, c, generator=g)))
+        dz = gy * (act > 0)
+    dxref, dgamma, dbeta = R.bn_bwd_ref(dz, x, mean, invstd, gamma)
+    s12 = torch.zeros(2 * c, device=cuda)
+    actd = act.to(cuda, BF) if act is not None else None
+    ops.bn_bwd_reduce(gy.to(cuda, BF), x.to(cuda, BF), coeffs, s12, mask_mode, act=actd)
+    dz_out = torch.empty(m, c, device=cuda, dtype=BF)
+    dy = ops.bn_bwd_apply(gy.to(cuda, BF), x.to(cuda, BF), coeffs, gamma.to(cuda), s12, m, mask_mode, act=actd,
+                          dz_out=dz_out)
+    torch.cuda.synchronize()
+    assert_close("bn_bwd_dbeta", s12[:c], dbeta, atol=1e-3 * float(dbeta.abs().max()) + 1e-4, rtol=1e-4)
+    assert_close("bn_bwd_dgamma", s12[c:], dgamma, atol=1e-3 * float(dgamma.abs().max()) + 1e-4, rtol=1e-4)
+    assert_close("bn_bwd_dx", dy, dxref, atol=1e-2 * float(dxref.abs().max()), rtol=1e-2)
+    assert_close("bn_bwd_dz", dz_out, dz, atol=0, rtol=0)
+
+
+def test_col_sum(cuda):
+    from byol_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(333, 1000, generator=g)
+    out = torch.zeros(1000, device=cuda)
+    ops.col_sum(x.to(cuda), out)
+    outb = torch.zeros(1000, device=cuda)
+    ops.col_sum(R.bf16_round(x).to(cuda, BF), outb)
+    torch.cuda.synchronize()
+    assert_close("col_sum_f32", out, x.sum(0), atol=1e-3, rtol=1e-4)
+    assert_close("col_sum_bf16", outb, R.bf16_round(x).sum(0), atol=1e-3, rtol=1e-4)
+
+
+def test_layout_and_weights(cuda):
+    from byol_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(3, 3, 10, 12, generator=g)
+    y = ops.nchw_to_nhwc8(x.to(cuda))
+    torch.cuda.synchronize()
+    ref = torch.zeros(3, 10, 12, 8)
+    ref[..., :3] = x.permute(0, 2, 3, 1)
+    assert_close("nchw_to_nhwc8", y, R.bf16_round(ref), atol=0, rtol=0)
+    w = torch.randn(16, 5, 3, 3, generator=g)
+    wf, wd = ops.prep_weight(w.to(cuda), cpad=8)
+    torch.cuda.synchronize()
+    reff = torch.zeros(16, 3, 3, 8)
+    reff[..., :5] = w.permute(0, 2, 3, 1)
+    assert_close("prep_weight_fprop", wf.view(16, 3, 3, 8), R.bf16_round(reff), atol=0, rtol=0)
+    refd = w.permute(1, 2, 3, 0).contiguous()  # [cin, kh, kw, cout]
+    assert_close("prep_weight_dgrad", wd.view(5, 3, 3, 16), R.bf16_round(refd), atol=0, rtol=0)
+
+
+def test_pooling(cuda):
+    from byol_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    x = R.bf16_round(torch.relu(torch.randn(2, 12, 12, 16, generator=g)))  # ties at zero like post-ReLU maps
+    y, idx = ops.maxpool_fwd(x.to(cuda, BF))
+    torch.cuda.synchronize()
+    yref, _ = R.maxpool_ref(x)
+    assert_close("maxpool_fwd", y, yref, atol=0, rtol=0)
+    dy = R.bf16_round(torch.randn(2, 6, 6, 16, generator=g))
+    dx = ops.maxpool_bwd(dy.to(cuda, BF), idx, 12, 12)
+    torch.cuda.synchronize()
+    assert_close("maxpool_bwd", dx, R.maxpool_bwd_ref(x, dy), atol=2e-2, rtol=1e-2)
+    a = R.bf16_round(torch.randn(5, 7, 7, 64, generator=g))
+    yf, yb = ops.avgpool_fwd(a.to(cuda, BF))
+    torch.cuda.synchronize()
+    assert_close("avgpool_fwd", yf, a.mean((1, 2)), atol=1e-5, rtol=1e-5)
+    assert_close("avgpool_fwd_bf16", yb, a.mean((1, 2)), atol=1e-2, rtol=1e-2)
+    gb = R.bf16_round(torch.randn(5, 64, generator=g))
+    gf = torch.randn(5, 64, generator=g)
+    dxa = ops.avgpool_bwd(gb.to(cuda, BF), gf.to(cuda), 5, 7, 7, 64)
+    torch.cuda.synchronize()
+    assert_close("avgpool_bwd", dxa, ((gb + gf) / 49)[:, None, None, :].expand(5, 7, 7, 64), atol=1e-3, rtol=1e-2)
+
+
+def _loss_ref(q1, q2, z1, z2):
+    # /root/reference/objective.py:6-25 restated (Frobenius norms of the whole matrices, no per-row normalisation)
+    def reg(x, y):
+        return -2 * torch.sum(x * y, dim=-1) / (x.norm() * y.norm())
+    return torch.mean(reg(q1, z2.detach()) + reg(q2, z1.detach()))
+
+
+@pytest.mark.parametrize("rows", [8, 256, 512])
+def test_loss(cuda, rows):
+    from byol_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    q1, q2, z1, z2 = [torch.randn(rows, 256, generator=g) for _ in range(4)]
+    q1r, q2r = q1.clone().requires_grad_(True), q2.clone().requires_grad_(True)
+    lref = _loss_ref(q1r, q2r, z1, z2)
+    (lref * 0.7).backward()
+    d = [t.to(cuda) for t in (q1, q2, z1, z2)]
+    ws = torch.empty(6, dtype=torch.float64, device=cuda)
+    loss = torch.empty(1, device=cuda)
+    saved = torch.empty(6, device=cuda)
+    ops.loss_fwd(*d, ws, loss, saved)
+    dq1, dq2 = torch.empty_like(d[0]), torch.empty_like(d[1])
+    go = torch.tensor([0.7], device=cuda)
+    ops.loss_bwd(*d, saved, go, dq1, dq2)
+    torch.cuda.synchronize()
+    assert_close("loss", loss, lref.detach().reshape(1), atol=1e-7, rtol=1e-5)
+    assert_close("loss_dq1", dq1, q1r.grad, atol=1e-9, rtol=1e-4)
+    assert_close("loss_dq2", dq2, q2r.grad, atol=1e-9, rtol=1e-4)
+
+
+@pytest.mark.parametrize("n", [1001, 4096, 1 << 20])
+def test_ema_bit_exact(cuda, n):
+    from byol_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(n + 4, generator=g)[:n].contiguous()
+    mean = torch.randn(n, generator=g)
+    # /root/reference/main.py:159-161: decay in float64 numpy, then (1 - decay) * x + decay * mean on fp32 tensors
+    step, total, base = 3, 1000, 0.996
+    decay = 1 - (1 - base) * (np.cos(np.pi * step / total) + 1) / 2.0
+    ref = (1 - decay) * x + decay * mean
+    md = mean.to(cuda)
+    ops.ema_update(x.to(cuda), md, np.float32(1 - decay), np.float32(decay))
+    torch.cuda.synchronize()
+    assert torch.equal(md.cpu(), ref), "EMA not bit-exact: max diff %g" % float((md.cpu() - ref).abs().max())
+
+
+def test_lars_sgd(cuda):
+    from byol_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    shapes = [(64, 3, 7, 7), (64,), (64,), (128, 64, 3, 3), (128,), (1000, 300), (1000,), (70000,)]
+    ignore = [0, 1, 1, 0, 1, 0, 1, 1]
+    params = [torch.randn(s, generator=g) * 0.1 for s in shapes]
+    params[4].zero_()  # zero-norm tensor: adaptive lr falls back to 1 (irrelevant for ignored, but exercise)
+    grads = [torch.randn(s, generator=g) * 0.01 for s in shapes]
+    lr, wd, trust, mom = 0.3, 1e-6, 0.001, 0.9
+    flat_p = torch.cat([p.reshape(-1) for p in params]).to(cuda)
+    flat_g = torch.cat([x.reshape(-1) for x in grads]).to(cuda)
+    flat_m = torch.zeros_like(flat_p)
+    CH = 4096
+    cs, cl, ct = [], [], []
+    off = 0
+    for t, p in enumerate(params):
+        nel = p.numel()
+        for s in range(0, nel, CH):
+            cs.append(off + s); cl.append(min(CH, nel - s)); ct.append(t)
+        off += nel
+    table = {
+        "chunk_start": torch.tensor(cs, dtype=torch.int64, device=cuda),
+        "chunk_len": torch.tensor(cl, dtype=torch.int32, device=cuda),
+        "chunk_tensor": torch.tensor(ct, dtype=torch.int32, device=cuda),
+        "wd": torch.tensor([0.0 if i else wd for i in ignore], device=cuda),
+        "lr": torch.full((len(shapes),), lr, device=cuda),
+        "ignore": torch.tensor(ignore, dtype=torch.int32, device=cuda),
+        "norms": torch.zeros(2 * len(shapes), dtype=torch.float64, device=cuda),
+    }
+    # reference: /root/reference/optimizers/lars.py:84-127 around torch.optim.SGD(momentum=0.9)
+    ref_p = [p.clone() for p in params]
+    ref_m = [None] * len(params)
+    for step in range(2):
+        ops.lars_sgd_step(flat_p, flat_g, flat_m, table, trust, 0.0, mom, first_step=(step == 0))
+        for i, p in enumerate(ref_p):
+            gr = grads[i].clone()
+            if not ignore[i]:
+                gr = gr.add(p, alpha=wd)
+                pn, gn = p.norm(), gr.norm()
+                alr = 1.0
+                if pn > 0 and gn > 0:
+                    alr = trust * pn / (gn + 0.0)
+                gr = gr.mul(alr)
+            ref_m[i] = gr.clone() if ref_m[i] is None else ref_m[i].mul(mom).add(gr)
+            p.add_(ref_m[i], alpha=-lr)
+    torch.cuda.synchronize()
+    assert_close("lars_params", flat_p, torch.cat([p.reshape(-1) for p in ref_p]), atol=1e-7, rtol=1e-5)
+    assert_close("lars_momentum", flat_m, torch.cat([m.reshape(-1) for m in ref_m]), atol=1e-9, rtol=1e-5)
