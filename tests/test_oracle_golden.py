@@ -1,0 +1,93 @@
+"""CPU: pin oracle/byol_oracle.py against golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py ran /root/reference's main.execute_graph / main.BYOL / objective / LARS)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import byol_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _sample_index(numel, n=4096, seed=12345):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, numel, (n,), generator=g)
+
+
+def _batches(seed, steps, b, r):
+    g = torch.Generator().manual_seed(seed + 1000)
+    return [(torch.rand(b, 3, r, r, generator=g), torch.rand(b, 3, r, r, generator=g),
+             torch.randint(0, 1000, (b,), generator=g)) for _ in range(steps)]
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    arch, rep, b, r, steps, seed, lr, total = z["config"]
+    return z, arch, int(rep), int(b), int(r), int(steps), int(seed), float(lr), int(total)
+
+
+@pytest.mark.parametrize("name", ["rn18_b8_r64", "rn50_b8_r64"])
+def test_oracle_matches_reference_golden(name):
+    torch.set_num_threads(8)
+    z, arch, rep, b, r, steps, seed, lr, total = load_case(name)
+    params, buffers = O.init_reference_state(arch, seed)
+    assert list(params.keys()) == list(z["param_names"])          # Q3: flat order = registration order
+    theta0 = torch.cat([p.reshape(-1) for p in params.values()])
+    assert theta0.numel() == int(z["numel"]) and len(params) == int(z["ntensors"])
+    idx = _sample_index(theta0.numel())
+    assert np.array_equal(theta0[idx].numpy(), z["theta0_sample"])  # identical init (bit-exact)
+    model = O.OracleBYOL(arch, params, buffers, total)
+    # Q4: target starts as 0.004 * theta0 and the step counter is already 1
+    assert int(z["ema0_step"]) == 1 and model.ema_step == 1
+    assert np.array_equal(model.ema_mean[idx].numpy(), z["ema0_sample"])
+    for s, (a1, a2, lab) in enumerate(_batches(seed, steps, b, r)):
+        res = model.train_step(a1, a2, lab, lr)
+        pre = "s%d_" % s
+        np.testing.assert_allclose(res["byol_loss"].item(), float(z[pre + "byol_loss"]), rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(res["ce_loss"].item(), float(z[pre + "ce_loss"]), rtol=2e-5)
+        np.testing.assert_allclose(res["loss"].item(), float(z[pre + "loss"]), rtol=2e-5)
+        for key in ("online_prediction1", "online_projection2", "target_projection1", "target_projection2",
+                    "online_representation1", "target_representation2"):
+            ref = z[pre + key]
+            np.testing.assert_allclose(res[key].numpy(), ref, rtol=1e-3, atol=1e-4 * np.abs(ref).max(), err_msg=key)
+        gflat = torch.cat([g.reshape(-1) for g in res["grads"].values()])
+        ref = z[pre + "grad_sample"]
+        np.testing.assert_allclose(gflat[idx].numpy(), ref, rtol=1e-3, atol=1e-4 * np.abs(ref).max())
+        np.testing.assert_allclose(gflat.double().norm().item(), float(z[pre + "grad_norm"]), rtol=1e-4)
+        np.testing.assert_allclose(model.flat_params()[idx].numpy(), z[pre + "theta_sample"], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(model.ema_mean[idx].numpy(), z[pre + "ema_sample"], rtol=1e-5, atol=1e-8)
+        assert model.ema_step == int(z[pre + "ema_step"])            # EMA bookkeeping bit-exact
+        mom = torch.cat([m.reshape(-1) for m in model.momentum_buf.values()])
+        ref = z[pre + "momentum_sample"]
+        np.testing.assert_allclose(mom[idx].numpy(), ref, rtol=1e-3, atol=1e-4 * np.abs(ref).max())
+        # Q7: BN running statistics are updated 4x per step
+        assert int(model.buffers["base_network.1.num_batches_tracked"]) == int(z[pre + "bn1_num_batches"]) == 4 * (s + 1)
+        np.testing.assert_allclose(model.buffers["base_network.1.running_mean"].numpy(), z[pre + "bn1_running_mean"],
+                                   rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(model.buffers["base_network.1.running_var"].numpy(), z[pre + "bn1_running_var"],
+                                   rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(model.buffers["head.1.running_var"].numpy()[:64], z[pre + "headbn_running_var"],
+                                   rtol=1e-3, atol=1e-6)
+
+
+def test_loss_is_frobenius_normalised():
+    """Q1/Q2: objective.py:8 normalises by the whole-matrix norm (value ~ -0.007 for random inputs, not ~4)."""
+    g = torch.Generator().manual_seed(0)
+    q1, q2, z1, z2 = [torch.randn(32, 256, generator=g) for _ in range(4)]
+    val = O.loss_function(q1, q2, z1, z2).item()
+    assert abs(val) < 0.05
+    manual = (-2 * (q1 * z2).sum() / (q1.norm() * z2.norm()) - 2 * (q2 * z1).sum() / (q2.norm() * z1.norm())) / 32
+    np.testing.assert_allclose(val, manual.item(), rtol=1e-5)
+
+
+def test_ema_bit_pattern():
+    """Q5: three separately rounded fp32 ops; an FMA/lerp form differs in the last bit."""
+    g = torch.Generator().manual_seed(1)
+    x, m = torch.randn(100000, generator=g), torch.randn(100000, generator=g)
+    d = O.cos_ema_decay(3, 1000, 0.996)
+    ref = (1 - d) * x + d * m
+    a, b = np.float32(1 - d), np.float32(d)
+    manual = (x.numpy() * a).astype(np.float32) + (m.numpy() * b).astype(np.float32)
+    assert np.array_equal(ref.numpy(), manual)
