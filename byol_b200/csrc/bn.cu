@@ -229,8 +229,17 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ g, const bf16* __re
                                     const float* __restrict__ shift, const float* __restrict__ mean,
                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
                                     const float* __restrict__ s1, const float* __restrict__ s2, float inv_count,
-                                    bf16* __restrict__ dy, bf16* __restrict__ dz_out, int64_t nvec, int C) {
+                                    bf16* __restrict__ dy, bf16* __restrict__ dz_out, int64_t nvec, int C,
+                                    const float* __restrict__ s1_local, const float* __restrict__ s2_local,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int groups = C >> 3;
+  if (blockIdx.x == 0 && dgamma != nullptr) {
+    // parameter gradients come from the rank-LOCAL sums (SyncBatchNorm.backward, _functions.py:122-170)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      dgamma[c] += s2_local[c];
+      dbeta[c] += s1_local[c];
+    }
+  }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const int gi = (int)(i % groups);
     float gv[8], xv[8];
@@ -344,21 +353,24 @@ extern "C" int byol_bn_bwd_reduce(const void* g, const void* x, const void* act,
   return check_launch("bn_bwd_reduce_kernel");
 }
 
+// s12: global (cross-rank) sums used for dy; s12_local: this rank's sums accumulated into dgamma/dbeta
+// (both optional; s12_local == nullptr means "same as s12").
 extern "C" int byol_bn_bwd_apply(const void* g, const void* x, const void* act, const float* scale,
                                  const float* shift, const float* mean, const float* invstd, const float* gamma,
                                  const float* s12, double count, void* dy, void* dz_out, int M, int C, int mask_mode,
-                                 cudaStream_t stream) {
+                                 const float* s12_local, float* dgamma, float* dbeta, cudaStream_t stream) {
+  if (s12_local == nullptr) s12_local = s12;
   BYOL_CHECK_ARG(g && x && mean && invstd && gamma && s12 && dy && M > 0 && C % 8 == 0, "byol_bn_bwd_apply: bad args");
   const int64_t nvec = (int64_t)M * C / 8;
   const float inv_count = (float)(1.0 / count);
   const bf16 *gp = (const bf16*)g, *xp = (const bf16*)x, *ap = (const bf16*)act;
   const int grid = grid_for(nvec, 256);
   if (mask_mode == 0)
-    bn_bwd_apply_kernel<0><<<grid, 256, 0, stream>>>(gp, xp, ap, scale, shift, mean, invstd, gamma, s12, s12 + C, inv_count, (bf16*)dy, (bf16*)dz_out, nvec, C);
+    bn_bwd_apply_kernel<0><<<grid, 256, 0, stream>>>(gp, xp, ap, scale, shift, mean, invstd, gamma, s12, s12 + C, inv_count, (bf16*)dy, (bf16*)dz_out, nvec, C, s12_local, s12_local + C, dgamma, dbeta);
   else if (mask_mode == 1)
-    bn_bwd_apply_kernel<1><<<grid, 256, 0, stream>>>(gp, xp, ap, scale, shift, mean, invstd, gamma, s12, s12 + C, inv_count, (bf16*)dy, (bf16*)dz_out, nvec, C);
+    bn_bwd_apply_kernel<1><<<grid, 256, 0, stream>>>(gp, xp, ap, scale, shift, mean, invstd, gamma, s12, s12 + C, inv_count, (bf16*)dy, (bf16*)dz_out, nvec, C, s12_local, s12_local + C, dgamma, dbeta);
   else
-    bn_bwd_apply_kernel<2><<<grid, 256, 0, stream>>>(gp, xp, ap, scale, shift, mean, invstd, gamma, s12, s12 + C, inv_count, (bf16*)dy, (bf16*)dz_out, nvec, C);
+    bn_bwd_apply_kernel<2><<<grid, 256, 0, stream>>>(gp, xp, ap, scale, shift, mean, invstd, gamma, s12, s12 + C, inv_count, (bf16*)dy, (bf16*)dz_out, nvec, C, s12_local, s12_local + C, dgamma, dbeta);
   return check_launch("bn_bwd_apply_kernel");
 }
 

@@ -106,25 +106,27 @@ __global__ void ema_kernel(const float* __restrict__ x, float* __restrict__ mean
 }
 
 // ---------------------------------------------------------------------------------------------
-// LARS + SGD momentum over a flat parameter buffer.
-// The buffer is described by a chunk table: chunk j covers elements [chunk_start[j], chunk_start[j]+chunk_len[j])
-// of tensor chunk_tensor[j].  Per tensor t: wd[t], lr[t], ignore[t] (1 = bias/BN: no LARS scaling).
-// Pass 1: norms[2t] += |p|^2, norms[2t+1] += |g + wd*p|^2 (fp64 atomics).  Pass 2: update.
+// Multi-tensor LARS + SGD momentum.
+// Tensors are described by device pointer tables p_ptrs/g_ptrs/m_ptrs[t]; work is split by a chunk table:
+// chunk j covers elements [chunk_start[j], chunk_start[j] + chunk_len[j]) of tensor chunk_tensor[j].
+// Per tensor t: wd[t], lr[t], ignore[t] (1 = bias/BN: weight decay only if wd>0, no LARS scaling).
+// Pass 1: norms[2t] += |p|^2, norms[2t+1] += |g + wd*p|^2 (fp64 atomics).  Pass 2: the update.
 // ---------------------------------------------------------------------------------------------
-__global__ void lars_norms_kernel(const float* __restrict__ p, const float* __restrict__ g,
+__global__ void lars_norms_kernel(const uint64_t* __restrict__ p_ptrs, const uint64_t* __restrict__ g_ptrs,
                                   const int64_t* __restrict__ chunk_start, const int* __restrict__ chunk_len,
                                   const int* __restrict__ chunk_tensor, const float* __restrict__ wd,
                                   const int* __restrict__ ignore, double* __restrict__ norms) {
   const int j = blockIdx.x;
   const int t = chunk_tensor[j];
   if (ignore[t]) return;   // norms unused for ignored tensors
-  const int64_t s = chunk_start[j];
+  const float* __restrict__ p = reinterpret_cast<const float*>(p_ptrs[t]) + chunk_start[j];
+  const float* __restrict__ g = reinterpret_cast<const float*>(g_ptrs[t]) + chunk_start[j];
   const int len = chunk_len[j];
   const float w = wd[t];
   float ap = 0.f, ag = 0.f;
   for (int i = threadIdx.x; i < len; i += blockDim.x) {
-    const float pv = p[s + i];
-    float gv = g[s + i];
+    const float pv = p[i];
+    float gv = g[i];
     if (w > 0.f) gv = gv + w * pv;
     ap += pv * pv;
     ag += gv * gv;
@@ -148,15 +150,17 @@ __global__ void lars_norms_kernel(const float* __restrict__ p, const float* __re
   }
 }
 
-__global__ void lars_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom,
-                                   const int64_t* __restrict__ chunk_start, const int* __restrict__ chunk_len,
-                                   const int* __restrict__ chunk_tensor, const float* __restrict__ wd,
-                                   const float* __restrict__ lr, const int* __restrict__ ignore,
-                                   const double* __restrict__ norms, float trust_coef, float eps, float momentum,
-                                   int first_step) {
+__global__ void lars_update_kernel(const uint64_t* __restrict__ p_ptrs, const uint64_t* __restrict__ g_ptrs,
+                                   const uint64_t* __restrict__ m_ptrs, const int64_t* __restrict__ chunk_start,
+                                   const int* __restrict__ chunk_len, const int* __restrict__ chunk_tensor,
+                                   const float* __restrict__ wd, const float* __restrict__ lr,
+                                   const int* __restrict__ ignore, const double* __restrict__ norms,
+                                   float trust_coef, float eps, float momentum, int first_step) {
   const int j = blockIdx.x;
   const int t = chunk_tensor[j];
-  const int64_t s = chunk_start[j];
+  float* __restrict__ p = reinterpret_cast<float*>(p_ptrs[t]) + chunk_start[j];
+  const float* __restrict__ g = reinterpret_cast<const float*>(g_ptrs[t]) + chunk_start[j];
+  float* __restrict__ mom = m_ptrs != nullptr ? reinterpret_cast<float*>(m_ptrs[t]) + chunk_start[j] : nullptr;
   const int len = chunk_len[j];
   const float w = wd[t];
   const float rate = lr[t];
@@ -167,13 +171,16 @@ __global__ void lars_update_kernel(float* __restrict__ p, const float* __restric
     if (pn > 0.f && gn > 0.f) ratio = trust_coef * pn / (gn + eps);
   }
   for (int i = threadIdx.x; i < len; i += blockDim.x) {
-    const float pv = p[s + i];
-    float gv = g[s + i];
+    const float pv = p[i];
+    float gv = g[i];
     if (w > 0.f) gv = gv + w * pv;
     gv = gv * ratio;
-    float b = first_step ? gv : momentum * mom[s + i] + gv;
-    mom[s + i] = b;
-    p[s + i] = pv - rate * b;
+    float b = gv;
+    if (mom != nullptr) {
+      b = first_step ? gv : momentum * mom[i] + gv;
+      mom[i] = b;
+    }
+    p[i] = pv - rate * b;
   }
 }
 
@@ -221,20 +228,21 @@ extern "C" int byol_ema_update(const float* x, float* mean, float one_minus_deca
   return check_launch("ema_kernel");
 }
 
-extern "C" int byol_lars_sgd_step(float* params, const float* grads, float* momentum_buf, const int64_t* chunk_start,
-                                  const int* chunk_len, const int* chunk_tensor, int num_chunks, const float* wd,
-                                  const float* lr, const int* ignore, int num_tensors, double* norms,
-                                  float trust_coef, float eps, float momentum, int first_step,
-                                  cudaStream_t stream) {
-  BYOL_CHECK_ARG(params && grads && momentum_buf && chunk_start && chunk_len && chunk_tensor && wd && lr && ignore && norms,
+// p_ptrs/g_ptrs/m_ptrs: device arrays of num_tensors fp32 pointers (m_ptrs may be null: no momentum).
+extern "C" int byol_lars_sgd_step(const void* p_ptrs, const void* g_ptrs, const void* m_ptrs,
+                                  const int64_t* chunk_start, const int* chunk_len, const int* chunk_tensor,
+                                  int num_chunks, const float* wd, const float* lr, const int* ignore,
+                                  int num_tensors, double* norms, float trust_coef, float eps, float momentum,
+                                  int first_step, cudaStream_t stream) {
+  BYOL_CHECK_ARG(p_ptrs && g_ptrs && chunk_start && chunk_len && chunk_tensor && wd && lr && ignore && norms,
                  "byol_lars_sgd_step: null pointer");
   BYOL_CHECK_ARG(num_chunks > 0 && num_tensors > 0, "byol_lars_sgd_step: empty");
   cudaError_t e = cudaMemsetAsync(norms, 0, 2 * (size_t)num_tensors * sizeof(double), stream);
   if (e != cudaSuccess) { set_last_error("byol_lars_sgd_step: memset failed: %s", cudaGetErrorString(e)); return -2; }
-  lars_norms_kernel<<<num_chunks, 256, 0, stream>>>(params, grads, chunk_start, chunk_len, chunk_tensor, wd, ignore,
-                                                   norms);
-  lars_update_kernel<<<num_chunks, 256, 0, stream>>>(params, grads, momentum_buf, chunk_start, chunk_len,
-                                                    chunk_tensor, wd, lr, ignore, norms, trust_coef, eps, momentum,
-                                                    first_step);
+  lars_norms_kernel<<<num_chunks, 256, 0, stream>>>((const uint64_t*)p_ptrs, (const uint64_t*)g_ptrs, chunk_start,
+                                                   chunk_len, chunk_tensor, wd, ignore, norms);
+  lars_update_kernel<<<num_chunks, 256, 0, stream>>>((const uint64_t*)p_ptrs, (const uint64_t*)g_ptrs,
+                                                    (const uint64_t*)m_ptrs, chunk_start, chunk_len, chunk_tensor,
+                                                    wd, lr, ignore, norms, trust_coef, eps, momentum, first_step);
   return check_launch("lars kernels");
 }

@@ -1,0 +1,474 @@
+"""Step engine: walks the (torchvision-shaped) module tree of :class:`byol_b200.model.BYOL`, keeps every
+parameter / gradient in flat fp32 buffers, and runs the BYOL forward and backward as explicit sequences of the
+sm_100a kernels in ``ops`` — no autograd graph, no ATen compute on the hot path.
+
+Reference semantics reproduced (file:line are /root/reference):
+
+* main.py:229-240  prediction(): encoder -> view(-1, C) -> head -> predictor
+* main.py:242-247  four passes per step in the order online(v1), online(v2), target(v1), target(v2); here they
+                   run layer by layer in lock-step ("lanes") so BN running statistics see the same update order
+                   per layer while weights stay hot in L2 and, under SyncBatchNorm, ONE
+                   all-reduce per layer carries the statistics of all lanes
+* main.py:214-227  target passes evaluate the same graph at the EMA weights (flat `target_network.mean`); no
+                   activations are kept for them
+* main.py:433      SyncBatchNorm: cross-rank sum of (sum, sum of squares) [fwd] and (sum dz, sum dz*xhat) [bwd]
+* main.py:440,617  DDP: gradients are averaged over ranks once per backward (one flat all-reduce)
+
+Data layout: activations NHWC bf16; conv outputs are stored raw ("y") and normalised copies ("a") are
+materialised by a fused BN-apply(+residual)+ReLU kernel; BN statistics come from the conv epilogue.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import ops
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+class _Unit(object):
+    """One conv/linear (+ optional BN) layer: static geometry plus offsets into the flat parameter vector."""
+    __slots__ = ("idx", "kind", "cin", "cout", "cpad", "k", "stride", "pad", "w_off", "w_numel", "b_off", "bn",
+                 "g_off", "beta_off", "name", "want_dgrad")
+
+
+class _Block(object):
+    __slots__ = ("kind", "c1", "c2", "c3", "down")
+
+
+class _Weights(object):
+    """bf16 tensor-core layouts of one weight set (online or target)."""
+
+    def __init__(self, units, device, want_dgrad):
+        nf = sum(u.cout * u.k * u.k * u.cpad for u in units)
+        self.pool_f = torch.empty(nf, dtype=BF16, device=device)
+        self.wf, self.wd = [], []
+        off = 0
+        for u in units:
+            n = u.cout * u.k * u.k * u.cpad
+            self.wf.append(self.pool_f[off:off + n].view(u.cout, u.k * u.k * u.cpad))
+            off += n
+        if want_dgrad:
+            nd = sum(u.cin * u.k * u.k * u.cout for u in units if u.want_dgrad)
+            self.pool_d = torch.empty(nd, dtype=BF16, device=device)
+            off = 0
+            for u in units:
+                if u.want_dgrad:
+                    n = u.cin * u.k * u.k * u.cout
+                    self.wd.append(self.pool_d[off:off + n].view(u.cin, u.k * u.k * u.cout))
+                    off += n
+                else:
+                    self.wd.append(None)
+        else:
+            self.wd = [None] * len(units)
+
+
+class Engine(object):
+    def __init__(self, model):
+        self.model = model
+        self.device = None
+        self.ready = False
+        self._bwd_cb_queued = False
+
+    # ------------------------------------------------------------------------------------------
+    # flat buffers
+    # ------------------------------------------------------------------------------------------
+    def flatten(self):
+        """(Re)build the flat parameter / gradient buffers and re-point every Parameter at its slice
+        (flat order = registration order, the reference's parameters_to_vector order, main.py:212,223)."""
+        model = self.model
+        params = list(model.parameters())
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("byol_b200.BYOL runs on CUDA only (sm_100a kernels; no CPU path): move the model "
+                               "to the GPU with .cuda() before calling it")
+        total = sum(p.numel() for p in params)
+        theta = torch.empty(total, dtype=F32, device=dev)
+        grad = torch.zeros(total, dtype=F32, device=dev)
+        self.offsets = {}
+        off = 0
+        for p in params:
+            n = p.numel()
+            theta[off:off + n].copy_(p.detach().reshape(-1).to(F32))
+            p.data = theta[off:off + n].view(p.shape)
+            p.grad = None
+            self.offsets[id(p)] = off
+            off += n
+        self.params = params
+        self.theta = theta
+        self.grad = grad
+        self.total = total
+        self.device = dev
+        ema = model.target_network
+        if ema.mean is None or ema.mean.numel() != total or ema.mean.device != dev:
+            ema.mean = torch.zeros(total, dtype=F32, device=dev) if ema.mean is None or ema.mean.numel() != total \
+                else ema.mean.to(dev)
+
+    def is_flat(self):
+        if self.device is None:
+            return False
+        base = self.theta.data_ptr()
+        for p in self.params:
+            if p.data_ptr() != base + 4 * self.offsets[id(p)]:
+                return False
+        return True
+
+    def attach_grads(self):
+        """Make p.grad a view into the flat gradient buffer (zeroing it first if grads were set to None)."""
+        if self.params[0].grad is None or self.params[0].grad.data_ptr() != self.grad.data_ptr():
+            self.grad.zero_()
+            for p in self.params:
+                off = self.offsets[id(p)]
+                p.grad = self.grad[off:off + p.numel()].view(p.shape)
+
+    def _gview(self, off, n):
+        return self.grad[off:off + n]
+
+    # ------------------------------------------------------------------------------------------
+    # plan
+    # ------------------------------------------------------------------------------------------
+    def _unit(self, mod, bn, name):
+        u = _Unit()
+        u.idx = len(self.units)
+        u.name = name
+        if isinstance(mod, nn.Conv2d):
+            assert mod.kernel_size[0] == mod.kernel_size[1] and mod.stride[0] == mod.stride[1]
+            assert mod.groups == 1 and mod.dilation[0] == 1 and mod.bias is None, "unsupported conv: %s" % name
+            u.kind, u.cin, u.cout = "conv", mod.in_channels, mod.out_channels
+            u.k, u.stride, u.pad = mod.kernel_size[0], mod.stride[0], mod.padding[0]
+            u.b_off = -1
+        else:
+            u.kind, u.cin, u.cout, u.k, u.stride, u.pad = "linear", mod.in_features, mod.out_features, 1, 1, 0
+            u.b_off = self.offsets[id(mod.bias)] if mod.bias is not None else -1
+        u.cpad = (u.cin + 7) // 8 * 8
+        u.w_off = self.offsets[id(mod.weight)]
+        u.w_numel = mod.weight.numel()
+        u.bn = bn
+        if bn is not None:
+            assert bn.affine and bn.track_running_stats and bn.momentum is not None, "unsupported BN: %s" % name
+            u.g_off, u.beta_off = self.offsets[id(bn.weight)], self.offsets[id(bn.bias)]
+        u.want_dgrad = u.cout % 8 == 0 and u.cin % 8 == 0
+        self.units.append(u)
+        return u
+
+    def build_plan(self):
+        model = self.model
+        self.units, self.blocks = [], []
+        children = list(model.base_network.children())
+        convs = [c for c in children if isinstance(c, nn.Conv2d)]
+        bns = [c for c in children if isinstance(c, nn.modules.batchnorm._BatchNorm)]
+        pools = [c for c in children if isinstance(c, nn.MaxPool2d)]
+        assert len(convs) == 1 and len(bns) == 1 and len(pools) == 1, "unexpected ResNet stem"
+        self.stem = self._unit(convs[0], bns[0], "stem")
+        self.stem.want_dgrad = False
+        mp = pools[0]
+        self.pool_k, self.pool_s, self.pool_p = mp.kernel_size, mp.stride, mp.padding
+        for layer in [c for c in children if isinstance(c, nn.Sequential)]:
+            for blk in layer.children():
+                b = _Block()
+                b.kind = "bottleneck" if hasattr(blk, "conv3") else "basic"
+                b.c1 = self._unit(blk.conv1, blk.bn1, "conv1")
+                b.c2 = self._unit(blk.conv2, blk.bn2, "conv2")
+                b.c3 = self._unit(blk.conv3, blk.bn3, "conv3") if b.kind == "bottleneck" else None
+                b.down = None
+                if blk.downsample is not None:
+                    d = list(blk.downsample.children())
+                    b.down = self._unit(d[0], d[1], "down")
+                self.blocks.append(b)
+        self.rep_dim = (self.blocks[-1].c3 or self.blocks[-1].c2).cout
+        self.mlps = []
+        for seq in (model.head, model.predictor):
+            l1, bn, _, l2 = list(seq.children())
+            self.mlps.append((self._unit(l1, bn, "l1"), self._unit(l2, None, "l2")))
+        self.cls = self._unit(model.linear_classifier, None, "classifier")
+        self.cls.want_dgrad = False
+        self.bn_modules = [u.bn for u in self.units if u.bn is not None]
+        self.sync = any(isinstance(b, nn.SyncBatchNorm) for b in self.bn_modules)
+        self.w_online = _Weights(self.units, self.device, True)
+        self.w_target = _Weights(self.units, self.device, False)
+        self.ready = True
+
+    def world(self):
+        return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+    def prep_weights(self, flat, wset, want_dgrad):
+        for u in self.units:
+            w = flat[u.w_off:u.w_off + u.w_numel].view(u.cout, u.cin, u.k, u.k)
+            ops.prep_weight(w, cpad=u.cpad, want_dgrad=want_dgrad and u.want_dgrad, out_f=wset.wf[u.idx],
+                            out_d=wset.wd[u.idx])
+
+    # ------------------------------------------------------------------------------------------
+    # forward building blocks (lists are per lane)
+    # ------------------------------------------------------------------------------------------
+    def _conv_bn(self, u, xs, lanes, train):
+        """raw conv/linear outputs + BN coefficients [scale, shift, mean, invstd] per lane."""
+        L, C = len(lanes), u.cout
+        stats = torch.zeros(L * 2 * C, dtype=F32, device=self.device) if train else None
+        ys = []
+        for i, (flat, wset, _) in enumerate(lanes):
+            st = stats[i * 2 * C:(i + 1) * 2 * C] if train else None
+            bias = flat[u.b_off:u.b_off + C] if u.b_off >= 0 else None
+            x = xs[i]
+            if u.kind == "linear":
+                y = ops.linear_fprop(x, wset.wf[u.idx], bias=bias, stats=st)
+            else:
+                y = ops.conv_fprop(x, wset.wf[u.idx], u.k, u.k, u.stride, u.pad, stats=st)
+            ys.append(y)
+        coeffs = torch.empty((L, 4, C), dtype=F32, device=self.device)
+        bn = u.bn
+        if train:
+            rows = ys[0].numel() // C
+            count = rows
+            if self.sync and self.world() > 1:
+                dist.all_reduce(stats)
+                count = rows * self.world()
+            for i, (flat, _, _) in enumerate(lanes):
+                ops.bn_finalize(stats[i * 2 * C:(i + 1) * 2 * C], count, flat[u.g_off:u.g_off + C],
+                                flat[u.beta_off:u.beta_off + C], bn.running_mean, bn.running_var, bn.momentum, bn.eps,
+                                coeffs[i])
+        else:
+            for i, (flat, _, _) in enumerate(lanes):
+                ops.bn_eval_coeffs(flat[u.g_off:u.g_off + C], flat[u.beta_off:u.beta_off + C], bn.running_mean,
+                                   bn.running_var, bn.eps, coeffs[i])
+        return ys, coeffs
+
+    @staticmethod
+    def _apply(y, c, relu, resid=None, rc=None):
+        C = y.shape[-1]
+        out = torch.empty_like(y)
+        ops.bn_apply(y.view(-1, C), c[0], c[1], relu, resid=None if resid is None else resid.view(-1, C),
+                     rscale=None if rc is None else rc[0], rshift=None if rc is None else rc[1], out=out.view(-1, C))
+        return out
+
+    def _block_fwd(self, b, xs, lanes, train):
+        L = len(lanes)
+        y1, c1 = self._conv_bn(b.c1, xs, lanes, train)
+        a1 = [self._apply(y1[i], c1[i], True) for i in range(L)]
+        y2, c2 = self._conv_bn(b.c2, a1, lanes, train)
+        if b.kind == "bottleneck":
+            a2 = [self._apply(y2[i], c2[i], True) for i in range(L)]
+            y3, c3 = self._conv_bn(b.c3, a2, lanes, train)
+            ylast, clast = y3, c3
+        else:
+            a2, y3, c3 = None, None, None
+            ylast, clast = y2, c2
+        if b.down is not None:
+            yd, cd = self._conv_bn(b.down, xs, lanes, train)
+            outs = [self._apply(ylast[i], clast[i], True, resid=yd[i], rc=cd[i]) for i in range(L)]
+        else:
+            yd, cd = None, None
+            outs = [self._apply(ylast[i], clast[i], True, resid=xs[i]) for i in range(L)]
+        for i, (_, _, saved) in enumerate(lanes):
+            if saved is not None:
+                saved["blocks"].append({
+                    "x": xs[i], "y1": y1[i], "c1": c1[i], "a1": a1[i], "y2": y2[i], "c2": c2[i],
+                    "a2": a2[i] if a2 is not None else None, "y3": y3[i] if y3 is not None else None,
+                    "c3": c3[i] if c3 is not None else None, "yd": yd[i] if yd is not None else None,
+                    "cd": cd[i] if cd is not None else None, "out": outs[i]})
+        return outs
+
+    def _mlp_fwd(self, mlp, xs, lanes, train, key):
+        l1, l2 = mlp
+        L = len(lanes)
+        h, c = self._conv_bn(l1, xs, lanes, train)
+        a = [self._apply(h[i], c[i], True) for i in range(L)]
+        outs_f, outs_b = [], []
+        for i, (flat, wset, saved) in enumerate(lanes):
+            o = ops.linear_fprop(a[i], wset.wf[l2.idx], bias=flat[l2.b_off:l2.b_off + l2.cout], out_fp32=True)
+            outs_f.append(o)
+            outs_b.append(ops.cast_bf16(o))
+            if saved is not None:
+                saved[key] = {"x": xs[i], "h": h[i], "c": c[i], "a": a[i]}
+        return outs_f, outs_b
+
+    def forward_lanes(self, augs, lanes, train, rep_bf16_out=None):
+        """augs: fp32 NCHW inputs per lane; lanes: (flat params, weight set, saved dict or None) per lane.
+        Returns per lane (representation fp32, projection fp32, prediction fp32)."""
+        L = len(lanes)
+        st = self.stem
+        x8 = [ops.nchw_to_nhwc8(a) for a in augs]
+        y0, c0 = self._conv_bn(st, x8, lanes, train)
+        a0 = [self._apply(y0[i], c0[i], True) for i in range(L)]
+        xs = []
+        for i, (_, _, saved) in enumerate(lanes):
+            p, idx = ops.maxpool_fwd(a0[i], self.pool_k, self.pool_s, self.pool_p, want_idx=saved is not None)
+            xs.append(p)
+            if saved is not None:
+                saved.update({"x8": x8[i], "y0": y0[i], "c0": c0[i], "a0_shape": tuple(a0[i].shape), "pool_idx": idx,
+                              "blocks": []})
+        del a0
+        for b in self.blocks:
+            xs = self._block_fwd(b, xs, lanes, train)
+        reps_f, reps_b = [], []
+        for i in range(L):
+            out_b = None
+            if rep_bf16_out is not None and rep_bf16_out[i] is not None:
+                out_b = rep_bf16_out[i]
+            n, h, w, c = xs[i].shape
+            yf = torch.empty((n, c), dtype=F32, device=self.device)
+            yb = out_b if out_b is not None else torch.empty((n, c), dtype=BF16, device=self.device)
+            ops.check(ops.lib.byol_avgpool_fwd(xs[i].data_ptr(), yf.data_ptr(), yb.data_ptr(), n, h * w, c,
+                                               ops._stream()), "byol_avgpool_fwd")
+            reps_f.append(yf)
+            reps_b.append(yb)
+            if lanes[i][2] is not None:
+                lanes[i][2]["final_shape"] = (n, h, w, c)
+        proj_f, proj_b = self._mlp_fwd(self.mlps[0], reps_b, lanes, train, "head")
+        pred_f, _ = self._mlp_fwd(self.mlps[1], proj_b, lanes, train, "pred")
+        if train:
+            torch._foreach_add_([b.num_batches_tracked for b in self.bn_modules], L)
+        return [(reps_f[i], proj_f[i], pred_f[i]) for i in range(L)], reps_b
+
+    # ------------------------------------------------------------------------------------------
+    # backward building blocks (online lanes only)
+    # ------------------------------------------------------------------------------------------
+    def _bn_bwd(self, u, gs, ys, cs, mask_mode, acts=None, want_dz=False):
+        L, C = len(gs), u.cout
+        s12 = torch.zeros(L * 2 * C, dtype=F32, device=self.device)
+        for i in range(L):
+            ops.bn_bwd_reduce(gs[i].view(-1, C), ys[i].view(-1, C), cs[i], s12[i * 2 * C:(i + 1) * 2 * C], mask_mode,
+                              act=None if acts is None else acts[i].view(-1, C))
+        rows = ys[0].numel() // C
+        count, local = rows, None
+        if self.sync and self.world() > 1:
+            local = s12.clone()
+            dist.all_reduce(s12)
+            count = rows * self.world()
+        gamma = self.theta[u.g_off:u.g_off + C]
+        dys, dzs = [], []
+        for i in range(L):
+            dz = torch.empty_like(ys[i]) if want_dz else None
+            dy = torch.empty_like(ys[i])
+            ops.bn_bwd_apply(gs[i].view(-1, C), ys[i].view(-1, C), cs[i], gamma, s12[i * 2 * C:(i + 1) * 2 * C], count,
+                             mask_mode, act=None if acts is None else acts[i].view(-1, C), dy=dy.view(-1, C),
+                             dz_out=None if dz is None else dz.view(-1, C),
+                             s12_local=None if local is None else local[i * 2 * C:(i + 1) * 2 * C],
+                             dgamma=self._gview(u.g_off, C), dbeta=self._gview(u.beta_off, C))
+            dys.append(dy)
+            dzs.append(dz)
+        return dys, dzs
+
+    def _wgrad(self, u, xs, dys):
+        dw = self._gview(u.w_off, u.w_numel).view(u.cout, u.cin, u.k, u.k)
+        for x, dy in zip(xs, dys):
+            if u.kind == "linear":
+                ops.conv_wgrad(x.view(x.shape[0], 1, 1, -1), dy.view(dy.shape[0], 1, 1, -1), dw, 1, 1, 1, 0)
+            else:
+                ops.conv_wgrad(x, dy, dw, u.k, u.k, u.stride, u.pad)
+
+    def _dgrad(self, u, dys, in_shapes, resids=None):
+        wd = self.w_online.wd[u.idx]
+        outs = []
+        for i, dy in enumerate(dys):
+            n, h, w, _ = in_shapes[i]
+            outs.append(ops.conv_dgrad(dy, wd, h, w, u.k, u.k, u.stride, u.pad,
+                                       resid=None if resids is None else resids[i]))
+        return outs
+
+    def _block_bwd(self, b, S, gs):
+        L = len(gs)
+        outs = [s["out"] for s in S]
+        xs = [s["x"] for s in S]
+        xshapes = [tuple(x.shape) for x in xs]
+        last = b.c3 if b.kind == "bottleneck" else b.c2
+        ylast = [s["y3"] if b.kind == "bottleneck" else s["y2"] for s in S]
+        clast = [s["c3"] if b.kind == "bottleneck" else s["c2"] for s in S]
+        dyl, dzs = self._bn_bwd(last, gs, ylast, clast, 2, acts=outs, want_dz=b.down is None)
+        if b.down is not None:
+            dyd, _ = self._bn_bwd(b.down, gs, [s["yd"] for s in S], [s["cd"] for s in S], 2, acts=outs)
+            self._wgrad(b.down, xs, dyd)
+            resid = self._dgrad(b.down, dyd, xshapes)
+        else:
+            resid = dzs
+        if b.kind == "bottleneck":
+            self._wgrad(b.c3, [s["a2"] for s in S], dyl)
+            g2 = self._dgrad(b.c3, dyl, [tuple(s["a2"].shape) for s in S])
+            dy2, _ = self._bn_bwd(b.c2, g2, [s["y2"] for s in S], [s["c2"] for s in S], 1)
+        else:
+            dy2 = dyl
+        self._wgrad(b.c2, [s["a1"] for s in S], dy2)
+        g1 = self._dgrad(b.c2, dy2, [tuple(s["a1"].shape) for s in S])
+        dy1, _ = self._bn_bwd(b.c1, g1, [s["y1"] for s in S], [s["c1"] for s in S], 1)
+        self._wgrad(b.c1, xs, dy1)
+        return self._dgrad(b.c1, dy1, xshapes, resids=resid)
+
+    def _mlp_bwd(self, mlp, S, douts):
+        """douts: per lane fp32 or bf16 [b, out] gradient of the MLP output; returns bf16 grads of its input."""
+        l1, l2 = mlp
+        L = len(S)
+        dbs = []
+        for i in range(L):
+            d = douts[i]
+            ops.col_sum(d, self._gview(l2.b_off, l2.cout))
+            dbs.append(ops.cast_bf16(d) if d.dtype == F32 else d)
+        self._wgrad(l2, [s["a"] for s in S], dbs)
+        das = [ops.linear_dgrad(dbs[i], self.w_online.wd[l2.idx]) for i in range(L)]
+        dhs, _ = self._bn_bwd(l1, das, [s["h"] for s in S], [s["c"] for s in S], 1)
+        for i in range(L):
+            ops.col_sum(dhs[i], self._gview(l1.b_off, l1.cout))
+        self._wgrad(l1, [s["x"] for s in S], dhs)
+        return [ops.linear_dgrad(dhs[i], self.w_online.wd[l1.idx]) for i in range(L)]
+
+    def backward_online(self, saved, d_reps, d_projs, d_preds):
+        """saved: per online view the dict filled by forward_lanes; d_*: fp32 grads (or None) of the outputs."""
+        self.notify_backward()
+        L = len(saved)
+        zero = lambda ref: torch.zeros_like(ref)
+        # predictor
+        if all(d is None for d in d_preds) and all(d is None for d in d_projs) and all(d is None for d in d_reps):
+            return
+        head_in = None
+        if any(d is not None for d in d_preds):
+            dq = [d if d is not None else zero(d_preds[[j for j in range(L) if d_preds[j] is not None][0]])
+                  for d in d_preds]
+            head_in = self._mlp_bwd(self.mlps[1], [s["pred"] for s in saved], [d.contiguous() for d in dq])
+        if any(d is not None for d in d_projs):
+            ref = [d for d in d_projs if d is not None][0]
+            extra = [d if d is not None else zero(ref) for d in d_projs]
+            head_in = [e.contiguous() if head_in is None else (head_in[i].float() + e) for i, e in enumerate(extra)]
+        rep_g = None
+        if head_in is not None:
+            rep_g = self._mlp_bwd(self.mlps[0], [s["head"] for s in saved], head_in)
+        if rep_g is None and all(d is None for d in d_reps):
+            return
+        gs = []
+        for i, s in enumerate(saved):
+            n, h, w, c = s["final_shape"]
+            du = d_reps[i].contiguous() if d_reps[i] is not None else None
+            gs.append(ops.avgpool_bwd(None if rep_g is None else rep_g[i], du, n, h, w, c))
+        for bi in range(len(self.blocks) - 1, -1, -1):
+            gs = self._block_bwd(self.blocks[bi], [s["blocks"][bi] for s in saved], gs)
+        g0 = []
+        for i, s in enumerate(saved):
+            n, h, w, c = s["a0_shape"]
+            g0.append(ops.maxpool_bwd(gs[i], s["pool_idx"], h, w, self.pool_k, self.pool_s, self.pool_p))
+        dy0, _ = self._bn_bwd(self.stem, g0, [s["y0"] for s in saved], [s["c0"] for s in saved], 1)
+        self._wgrad(self.stem, [s["x8"] for s in saved], dy0)
+
+    # classifier (stop-grad input; main.py:250-252)
+    def classifier_forward(self, rep_cat_b):
+        u = self.cls
+        flat = self.theta
+        return ops.linear_fprop(rep_cat_b, self.w_online.wf[u.idx], bias=flat[u.b_off:u.b_off + u.cout], out_fp32=True)
+
+    def classifier_backward(self, rep_cat_b, d_logits):
+        self.notify_backward()
+        u = self.cls
+        d = d_logits.contiguous()
+        ops.col_sum(d, self._gview(u.b_off, u.cout))
+        self._wgrad(u, [rep_cat_b], [ops.cast_bf16(d)])
+
+    # ------------------------------------------------------------------------------------------
+    # DDP: one flat gradient all-reduce (mean) when the backward pass finishes (main.py:440-443, 617)
+    # ------------------------------------------------------------------------------------------
+    def notify_backward(self):
+        self.attach_grads()
+        if not self._bwd_cb_queued:
+            self._bwd_cb_queued = True
+            torch.autograd.Variable._execution_engine.queue_callback(self._finish_backward)
+
+    def _finish_backward(self):
+        self._bwd_cb_queued = False
+        if self.world() > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.AVG)

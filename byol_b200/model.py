@@ -1,0 +1,208 @@
+"""Host-side mirror of the reference's model API (``/root/reference/main.py:133-276``): ``CosEMA`` and ``BYOL``
+with the same constructor arguments, attributes, ``state_dict`` keys and 13-key forward dict — but the compute
+runs in the sm_100a kernels of ``byol_b200`` through :class:`byol_b200.engine.Engine`.
+
+The nn.Module tree (torchvision ResNet children[:-1], head, predictor, linear_classifier) is kept only as the
+*container* of parameters and buffers, so ``named_parameters()``, ``state_dict()``, ``nn.SyncBatchNorm
+.convert_sync_batchnorm``, ``.cuda()`` and ``helpers.layers.add_weight_decay`` behave exactly as with the
+reference; none of the torch modules' ``forward`` methods is ever called.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torchvision.models as models
+
+from . import ops
+from .engine import Engine
+
+BF16 = torch.bfloat16
+
+
+class CosEMA(nn.Module):
+    """Flat-vector EMA with cosine-annealed decay — mirrors /root/reference/main.py:133-164.
+
+    ``mean`` is a registered buffer (checkpointed); ``step`` is a plain attribute (not checkpointed).
+    The update runs in place on ``mean`` with ``byol_ema_update`` (bit-exact with the reference's three fp32 ops).
+    """
+
+    def __init__(self, total_steps, base_decay=0.996):
+        super(CosEMA, self).__init__()
+        self.step = 0
+        self.total_steps = total_steps
+        self.base_decay = base_decay
+        self.register_buffer('mean', None)
+
+    def decay_at(self, step):
+        # numpy float64, exactly as main.py:159
+        return 1 - (1 - self.base_decay) * (np.cos(np.pi * step / self.total_steps) + 1) / 2.0
+
+    def forward(self, x):
+        if self.mean is None:
+            self.mean = torch.zeros_like(x)
+        if self.training:
+            if not x.is_cuda:
+                raise RuntimeError("byol_b200.CosEMA updates run on CUDA only (no CPU path)")
+            decay = self.decay_at(self.step)
+            ops.ema_update(x.detach(), self.mean, np.float32(1 - decay), np.float32(decay))
+            self.step += 1
+        return x
+
+
+def _resnet(arch):
+    if arch in models.__dict__:
+        return models.__dict__[arch](weights=None)
+    if arch == "resnet200":   # BASELINE.json config 5: bottleneck [3, 24, 36, 3]; not a torchvision constructor
+        from torchvision.models.resnet import ResNet, Bottleneck
+        return ResNet(Bottleneck, [3, 24, 36, 3])
+    raise ValueError("unknown arch %r" % arch)
+
+
+class _OnlineTargetFn(torch.autograd.Function):
+    """All four encoder passes of one step (main.py:244-247) as ONE autograd node.
+
+    Outputs 0-5: online (representation, projection, prediction) for view 1 and 2 — differentiable;
+    outputs 6-11: the same for the target network — non-differentiable (the loss detaches them anyway,
+    objective.py:23-24)."""
+
+    @staticmethod
+    def forward(ctx, model, aug1, aug2, anchor):
+        eng = model._engine
+        saved = [{}, {}]
+        lanes = [(eng.theta, eng.w_online, saved[0]), (eng.theta, eng.w_online, saved[1]),
+                 (model.target_network.mean, eng.w_target, None), (model.target_network.mean, eng.w_target, None)]
+        outs, reps_b = eng.forward_lanes([aug1, aug2, aug1, aug2], lanes, True,
+                                         rep_bf16_out=[model._rep_cat[:aug1.shape[0]], model._rep_cat[aug1.shape[0]:],
+                                                       None, None])
+        ctx.model = model
+        ctx.saved = saved
+        ctx.set_materialize_grads(False)
+        flat = [t for o in outs for t in o]
+        ctx.mark_non_differentiable(*flat[6:])
+        return tuple(flat)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        eng = ctx.model._engine
+        saved, ctx.saved = ctx.saved, None
+        eng.backward_online(saved, [grads[0], grads[3]], [grads[1], grads[4]], [grads[2], grads[5]])
+        return None, None, None, None
+
+
+class _ClassifierFn(torch.autograd.Function):
+    """Stop-gradient linear classifier (main.py:250-252): logits are differentiable w.r.t. its own weights only."""
+
+    @staticmethod
+    def forward(ctx, model, rep_cat_b, anchor):
+        ctx.model = model
+        ctx.rep = rep_cat_b
+        return model._engine.classifier_forward(rep_cat_b)
+
+    @staticmethod
+    def backward(ctx, d_logits):
+        ctx.model._engine.classifier_backward(ctx.rep, d_logits)
+        return None, None, None
+
+
+class BYOL(nn.Module):
+    """Drop-in for ``main.BYOL`` (/root/reference/main.py:167-276).
+
+    The reference reads ``args.arch`` / ``args.head_latent_size`` from a module global (main.py:190,195); here they
+    are keyword arguments with the reference's defaults (main.py:57,63)."""
+
+    def __init__(self, base_network_output_size, projection_output_size, classifier_output_size,
+                 total_training_steps, base_decay=0.996, arch="resnet50", head_latent_size=4096):
+        super(BYOL, self).__init__()
+        self.base_network_output_size = base_network_output_size
+        self.arch = arch
+        # identical construction order to main.py:190-208 => identical parameter order and default initialisation
+        self.base_network = nn.Sequential(*list(_resnet(arch).children())[:-1])
+        self.head = nn.Sequential(
+            nn.Linear(base_network_output_size, head_latent_size),
+            nn.BatchNorm1d(head_latent_size),
+            nn.ReLU(),
+            nn.Linear(head_latent_size, projection_output_size),
+        )
+        self.predictor = nn.Sequential(
+            nn.Linear(projection_output_size, head_latent_size),
+            nn.BatchNorm1d(head_latent_size),
+            nn.ReLU(),
+            nn.Linear(head_latent_size, projection_output_size),
+        )
+        self.linear_classifier = nn.Linear(base_network_output_size, classifier_output_size)
+        self.target_network = CosEMA(total_training_steps, base_decay)
+        # main.py:211-212 runs the EMA once at construction (mean = 0.004 * theta0, step -> 1).
+        # Construction happens on the host; the kernel-side update is deferred to the first use on the GPU.
+        total = sum(p.numel() for p in self.parameters())
+        self.target_network.mean = torch.zeros(total)
+        self._ema_init_pending = True
+        self._engine = Engine(self)
+        self._anchor = None
+        self._rep_cat = None
+
+    # ---- keep the engine in sync with module surgery (.cuda(), convert_sync_batchnorm, ...) ----
+    def _apply(self, fn, *args, **kwargs):
+        out = super(BYOL, self)._apply(fn, *args, **kwargs)
+        self._engine.ready = False
+        return out
+
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        out = super(BYOL, self).load_state_dict(state_dict, *args, **kwargs)
+        if "target_network.mean" in state_dict:
+            self._ema_init_pending = False    # a restored target network supersedes the construction-time init
+        return out
+
+    def _ensure_ready(self, batch):
+        eng = self._engine
+        if not eng.ready or not eng.is_flat():
+            eng.flatten()
+            eng.build_plan()
+        if self._ema_init_pending:
+            was = self.target_network.training
+            self.target_network.train()
+            self.target_network(eng.theta)
+            self.target_network.train(was)
+            self._ema_init_pending = False
+        if self._anchor is None or self._anchor.device != eng.device:
+            self._anchor = torch.zeros(1, device=eng.device, requires_grad=True)
+        if self._rep_cat is None or self._rep_cat.shape[0] != 2 * batch or self._rep_cat.device != eng.device:
+            self._rep_cat = torch.empty((2 * batch, eng.rep_dim), dtype=BF16, device=eng.device)
+        return eng
+
+    def parameters_vector(self):
+        """The flat fp32 vector of all parameters in registration order (what the reference builds with
+        nn.utils.parameters_to_vector at main.py:212,223,255) — here a persistent buffer, not a copy."""
+        return self._ensure_ready(1).theta if self._rep_cat is None else self._engine.theta
+
+    def forward(self, augmentation1, augmentation2):
+        """Returns the online and target network representations, projections and predictions (main.py:242-276)."""
+        if not augmentation1.is_cuda:
+            raise RuntimeError("byol_b200.BYOL.forward needs CUDA tensors (no CPU path)")
+        b = augmentation1.shape[0]
+        eng = self._ensure_ready(b)
+        a1 = augmentation1.contiguous().float()
+        a2 = augmentation2.contiguous().float()
+        eng.prep_weights(eng.theta, eng.w_online, want_dgrad=self.training)
+        eng.prep_weights(self.target_network.mean, eng.w_target, want_dgrad=False)
+        if self.training and torch.is_grad_enabled():
+            o = _OnlineTargetFn.apply(self, a1, a2, self._anchor)
+            rep_cat = self._rep_cat
+            linear_preds = _ClassifierFn.apply(self, rep_cat, self._anchor)
+        else:
+            lanes = [(eng.theta, eng.w_online, None), (eng.theta, eng.w_online, None),
+                     (self.target_network.mean, eng.w_target, None), (self.target_network.mean, eng.w_target, None)]
+            outs, reps_b = eng.forward_lanes([a1, a2, a1, a2], lanes, self.training,
+                                             rep_bf16_out=[self._rep_cat[:b], self._rep_cat[b:], None, None])
+            o = [t for oo in outs for t in oo]
+            rep_cat = self._rep_cat if self.training else self._rep_cat[:b]   # eval: view 1 only (main.py:250-251)
+            linear_preds = eng.classifier_forward(rep_cat)
+
+        # Update the EMA parameters with the pre-update online weights (main.py:254-255)
+        self.target_network(eng.theta)
+
+        return {
+            'linear_preds': linear_preds,
+            'online_representation1': o[0], 'online_projection1': o[1], 'online_prediction1': o[2],
+            'online_representation2': o[3], 'online_projection2': o[4], 'online_prediction2': o[5],
+            'target_representation1': o[6], 'target_projection1': o[7], 'target_prediction1': o[8],
+            'target_representation2': o[9], 'target_projection2': o[10], 'target_prediction2': o[11],
+        }

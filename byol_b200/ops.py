@@ -191,14 +191,18 @@ def bn_bwd_reduce(g, x, coeffs, s12, mask_mode, act=None):
     return s12
 
 
-def bn_bwd_apply(g, x, coeffs, gamma, s12, count, mask_mode, act=None, dy=None, dz_out=None):
+def bn_bwd_apply(g, x, coeffs, gamma, s12, count, mask_mode, act=None, dy=None, dz_out=None, s12_local=None,
+                 dgamma=None, dbeta=None):
+    """dy = gamma*invstd*(dz - s1/n - xhat*s2/n) with the (global) sums s12 over `count` rows; when dgamma/dbeta
+    are given they are incremented by the rank-local sums (s12_local, default s12)."""
     _chk(g, BF16, "g"); _chk(x, BF16, "x"); _chk(act, BF16, "act")
     m, c = x.shape
     if dy is None:
         dy = torch.empty_like(x)
     check(lib.byol_bn_bwd_apply(_ptr(g), _ptr(x), _ptr(act), _ptr(coeffs[0]), _ptr(coeffs[1]), _ptr(coeffs[2]),
                                 _ptr(coeffs[3]), _ptr(gamma), _ptr(s12), float(count), _ptr(dy), _ptr(dz_out), m, c,
-                                mask_mode, _stream()), "byol_bn_bwd_apply")
+                                mask_mode, _ptr(s12_local), _ptr(dgamma), _ptr(dbeta), _stream()),
+          "byol_bn_bwd_apply")
     return dy
 
 
@@ -277,12 +281,11 @@ def ema_update(x, mean, one_minus_decay, decay):
     return mean
 
 
-def lars_sgd_step(params, grads, mom, table, trust_coef, eps, momentum, first_step):
-    """table: dict with device tensors chunk_start(int64), chunk_len(int32), chunk_tensor(int32), wd, lr (fp32),
-    ignore (int32), norms (fp64 [2*T])."""
-    _chk(params, F32, "params"); _chk(grads, F32, "grads"); _chk(mom, F32, "mom")
-    check(lib.byol_lars_sgd_step(_ptr(params), _ptr(grads), _ptr(mom), _ptr(table["chunk_start"]),
-                                 _ptr(table["chunk_len"]), _ptr(table["chunk_tensor"]),
+def lars_sgd_step(table, trust_coef, eps, momentum, first_step):
+    """table: dict of device tensors p_ptrs/g_ptrs/m_ptrs (int64 pointer tables, m_ptrs may be None),
+    chunk_start (int64), chunk_len / chunk_tensor (int32), wd / lr (fp32), ignore (int32), norms (fp64 [2*T])."""
+    check(lib.byol_lars_sgd_step(_ptr(table["p_ptrs"]), _ptr(table["g_ptrs"]), _ptr(table.get("m_ptrs")),
+                                 _ptr(table["chunk_start"]), _ptr(table["chunk_len"]), _ptr(table["chunk_tensor"]),
                                  table["chunk_start"].numel(), _ptr(table["wd"]), _ptr(table["lr"]),
                                  _ptr(table["ignore"]), table["wd"].numel(), _ptr(table["norms"]),
                                  float(trust_coef), float(eps), float(momentum), int(first_step), _stream()),

@@ -75,9 +75,12 @@ def test_bn_backward(cuda, mask_mode, m, c):
     actd = act.to(cuda, BF) if act is not None else None
     ops.bn_bwd_reduce(gy.to(cuda, BF), x.to(cuda, BF), coeffs, s12, mask_mode, act=actd)
     dz_out = torch.empty(m, c, device=cuda, dtype=BF)
+    dgam, dbet = torch.ones(c, device=cuda), torch.ones(c, device=cuda)
     dy = ops.bn_bwd_apply(gy.to(cuda, BF), x.to(cuda, BF), coeffs, gamma.to(cuda), s12, m, mask_mode, act=actd,
-                          dz_out=dz_out)
+                          dz_out=dz_out, dgamma=dgam, dbeta=dbet)
     torch.cuda.synchronize()
+    assert_close("bn_bwd_dgamma_acc", dgam, 1 + dgamma, atol=1e-3 * float(dgamma.abs().max()) + 1e-4, rtol=1e-4)
+    assert_close("bn_bwd_dbeta_acc", dbet, 1 + dbeta, atol=1e-3 * float(dbeta.abs().max()) + 1e-4, rtol=1e-4)
     assert_close("bn_bwd_dbeta", s12[:c], dbeta, atol=1e-3 * float(dbeta.abs().max()) + 1e-4, rtol=1e-4)
     assert_close("bn_bwd_dgamma", s12[c:], dgamma, atol=1e-3 * float(dgamma.abs().max()) + 1e-4, rtol=1e-4)
     assert_close("bn_bwd_dx", dy, dxref, atol=1e-2 * float(dxref.abs().max()), rtol=1e-2)
@@ -203,9 +206,15 @@ def test_lars_sgd(cuda):
     for t, p in enumerate(params):
         nel = p.numel()
         for s in range(0, nel, CH):
-            cs.append(off + s); cl.append(min(CH, nel - s)); ct.append(t)
+            cs.append(s); cl.append(min(CH, nel - s)); ct.append(t)
         off += nel
+    offs = [0]
+    for p in params:
+        offs.append(offs[-1] + p.numel())
     table = {
+        "p_ptrs": torch.tensor([flat_p.data_ptr() + 4 * o for o in offs[:-1]], dtype=torch.int64, device=cuda),
+        "g_ptrs": torch.tensor([flat_g.data_ptr() + 4 * o for o in offs[:-1]], dtype=torch.int64, device=cuda),
+        "m_ptrs": torch.tensor([flat_m.data_ptr() + 4 * o for o in offs[:-1]], dtype=torch.int64, device=cuda),
         "chunk_start": torch.tensor(cs, dtype=torch.int64, device=cuda),
         "chunk_len": torch.tensor(cl, dtype=torch.int32, device=cuda),
         "chunk_tensor": torch.tensor(ct, dtype=torch.int32, device=cuda),
@@ -218,7 +227,7 @@ def test_lars_sgd(cuda):
     ref_p = [p.clone() for p in params]
     ref_m = [None] * len(params)
     for step in range(2):
-        ops.lars_sgd_step(flat_p, flat_g, flat_m, table, trust, 0.0, mom, first_step=(step == 0))
+        ops.lars_sgd_step(table, trust, 0.0, mom, first_step=(step == 0))
         for i, p in enumerate(ref_p):
             gr = grads[i].clone()
             if not ignore[i]:
