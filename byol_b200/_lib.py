@@ -81,6 +81,11 @@ def last_error():
     return lib.byol_last_error().decode("utf-8", "replace")
 
 
-def check(status, what):
+# number of byol_b200 CUDA kernels launched through the C-ABI since import (bench.py reports the per-step count)
+launch_count = [0]
+
+
+def check(status, what, kernels=1):
     if status != 0:
         raise ByolLibraryError("%s failed (status %d): %s" % (what, status, last_error()))
+    launch_count[0] += kernels

@@ -260,7 +260,7 @@ def loss_fwd(q1, q2, z1, z2, workspace, loss, saved):
         _chk(t, F32, nm)
     rows, dim = q1.shape
     check(lib.byol_loss_fwd(_ptr(q1), _ptr(q2), _ptr(z1), _ptr(z2), rows, dim, _ptr(workspace), _ptr(loss),
-                            _ptr(saved), _stream()), "byol_loss_fwd")
+                            _ptr(saved), _stream()), "byol_loss_fwd", kernels=2)
     return loss
 
 
@@ -289,4 +289,4 @@ def lars_sgd_step(table, trust_coef, eps, momentum, first_step):
                                  table["chunk_start"].numel(), _ptr(table["wd"]), _ptr(table["lr"]),
                                  _ptr(table["ignore"]), table["wd"].numel(), _ptr(table["norms"]),
                                  float(trust_coef), float(eps), float(momentum), int(first_step), _stream()),
-          "byol_lars_sgd_step")
+          "byol_lars_sgd_step", kernels=2)

@@ -101,6 +101,17 @@ def loss_function(online_prediction1, online_prediction2, target_projection1, ta
     return torch.mean(loss_ab + loss_ba)
 
 
+def _identity(t):
+    return t
+
+
+def bf16_storage(t):
+    """Round to bf16 with a straight-through gradient: emulates the CUDA path's bf16 activation / weight STORAGE
+    (fp32 accumulation everywhere), so that parity against the kernels can be asserted tightly.  The fp32 oracle
+    (storage='fp32') stays the reference-faithful one that is pinned against the golden vectors."""
+    return t + (t.detach().to(torch.bfloat16).to(torch.float32) - t.detach())
+
+
 class _BN(object):
     """torch.nn.functional.batch_norm with nn.BatchNorm's bookkeeping (momentum 0.1, eps 1e-5, unbiased running
     variance, num_batches_tracked += 1 per training call).  Under emulated SyncBatchNorm the caller passes the
@@ -116,43 +127,48 @@ class _BN(object):
         return F.batch_norm(x, rm, rv, P[prefix + ".weight"], P[prefix + ".bias"], train, self.momentum, self.eps)
 
 
-def encoder_forward(arch, P, bn, x, train, prefix="base_network"):
+def encoder_forward(arch, P, bn, x, train, prefix="base_network", trace=None, q=_identity):
     """torchvision ResNet (v1.5: stride on the 3x3) children[:-1] as an nn.Sequential: indices 0 conv1, 1 bn1,
     2 relu, 3 maxpool, 4-7 layer1-4, 8 avgpool (main.py:190-193, 237)."""
     kind, depths = ARCHS[arch]
-    x = F.conv2d(x, P[prefix + ".0.weight"], None, 2, 3)
-    x = torch.relu(bn(x, prefix + ".1", P, train))
+    conv = lambda inp, name, stride=1, pad=0: q(F.conv2d(inp, q(P[name]), None, stride, pad))
+    x = conv(q(x), prefix + ".0.weight", 2, 3)
+    x = q(torch.relu(bn(x, prefix + ".1", P, train)))
     x = F.max_pool2d(x, 3, 2, 1)
+    if trace is not None:
+        trace.append(("pool", x.detach()))
     for li, depth in enumerate(depths):
         for bi in range(depth):
             p = "%s.%d.%d" % (prefix, 4 + li, bi)
             stride = 2 if (li > 0 and bi == 0) else 1
             identity = x
             if kind == "bottleneck":
-                out = torch.relu(bn(F.conv2d(x, P[p + ".conv1.weight"]), p + ".bn1", P, train))
-                out = torch.relu(bn(F.conv2d(out, P[p + ".conv2.weight"], None, stride, 1), p + ".bn2", P, train))
-                out = bn(F.conv2d(out, P[p + ".conv3.weight"]), p + ".bn3", P, train)
+                out = q(torch.relu(bn(conv(x, p + ".conv1.weight"), p + ".bn1", P, train)))
+                out = q(torch.relu(bn(conv(out, p + ".conv2.weight", stride, 1), p + ".bn2", P, train)))
+                out = bn(conv(out, p + ".conv3.weight"), p + ".bn3", P, train)
             else:
-                out = torch.relu(bn(F.conv2d(x, P[p + ".conv1.weight"], None, stride, 1), p + ".bn1", P, train))
-                out = bn(F.conv2d(out, P[p + ".conv2.weight"], None, 1, 1), p + ".bn2", P, train)
+                out = q(torch.relu(bn(conv(x, p + ".conv1.weight", stride, 1), p + ".bn1", P, train)))
+                out = bn(conv(out, p + ".conv2.weight", 1, 1), p + ".bn2", P, train)
             if (p + ".downsample.0.weight") in P:
-                identity = bn(F.conv2d(x, P[p + ".downsample.0.weight"], None, stride), p + ".downsample.1", P, train)
-            x = torch.relu(out + identity)
+                identity = bn(conv(x, p + ".downsample.0.weight", stride), p + ".downsample.1", P, train)
+            x = q(torch.relu(out + identity))
+            if trace is not None:
+                trace.append((p, x.detach()))
     return x.mean((2, 3))  # AdaptiveAvgPool2d(1) + view(-1, C)  (main.py:237)
 
 
-def mlp_forward(P, bn, x, prefix, train):
+def mlp_forward(P, bn, x, prefix, train, q=_identity):
     """main.py:194-205: Linear -> BatchNorm1d -> ReLU -> Linear."""
-    h = F.linear(x, P[prefix + ".0.weight"], P[prefix + ".0.bias"])
-    h = torch.relu(bn(h, prefix + ".1", P, train))
-    return F.linear(h, P[prefix + ".3.weight"], P[prefix + ".3.bias"])
+    h = q(F.linear(q(x), q(P[prefix + ".0.weight"]), P[prefix + ".0.bias"]))
+    h = q(torch.relu(bn(h, prefix + ".1", P, train)))
+    return F.linear(h, q(P[prefix + ".3.weight"]), P[prefix + ".3.bias"])
 
 
-def prediction(arch, P, bn, aug, train):
+def prediction(arch, P, bn, aug, train, q=_identity):
     """main.py:229-240."""
-    representation = encoder_forward(arch, P, bn, aug, train)
-    projection = mlp_forward(P, bn, representation, "head", train)
-    pred = mlp_forward(P, bn, projection, "predictor", train)
+    representation = encoder_forward(arch, P, bn, aug, train, q=q)
+    projection = mlp_forward(P, bn, representation, "head", train, q=q)
+    pred = mlp_forward(P, bn, projection, "predictor", train, q=q)
     return representation, projection, pred
 
 
@@ -160,8 +176,10 @@ class OracleBYOL(object):
     """State + one-step semantics of main.BYOL + LARS(SGD) for `world` emulated data-parallel ranks."""
 
     def __init__(self, arch, params, buffers, total_training_steps, base_decay=0.996, weight_decay=1e-6,
-                 momentum=0.9, trust_coef=0.001, lars_eps=0.0):
+                 momentum=0.9, trust_coef=0.001, lars_eps=0.0, storage="fp32"):
         self.arch = arch
+        assert storage in ("fp32", "bf16")
+        self.q = bf16_storage if storage == "bf16" else _identity
         self.names = list(params.keys())
         self.params = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in params.items())
         self.buffers = OrderedDict((k, v.detach().clone()) for k, v in buffers.items())
@@ -195,14 +213,15 @@ class OracleBYOL(object):
     # ---- forward (main.py:242-276) ----------------------------------------------------------
     def forward(self, aug1, aug2, training=True):
         P = self.params
-        o1 = prediction(self.arch, P, self.bn, aug1, training)
-        o2 = prediction(self.arch, P, self.bn, aug2, training)
+        q = self.q
+        o1 = prediction(self.arch, P, self.bn, aug1, training, q)
+        o2 = prediction(self.arch, P, self.bn, aug2, training, q)
         T = self.target_params()
         with torch.no_grad():   # bit-identical to the reference's graph-building target passes (SURVEY.md §3.3 probe)
-            t1 = prediction(self.arch, T, self.bn, aug1, training)
-            t2 = prediction(self.arch, T, self.bn, aug2, training)
+            t1 = prediction(self.arch, T, self.bn, aug1, training, q)
+            t2 = prediction(self.arch, T, self.bn, aug2, training, q)
         rep = torch.cat([o1[0], o2[0]], 0) if training else o1[0]
-        linear_preds = F.linear(rep.clone().detach(), P["linear_classifier.weight"], P["linear_classifier.bias"])
+        linear_preds = F.linear(q(rep.clone().detach()), q(P["linear_classifier.weight"]), P["linear_classifier.bias"])
         if training:
             self._ema_update()
         return {
