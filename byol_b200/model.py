@@ -51,9 +51,12 @@ class CosEMA(nn.Module):
 def _resnet(arch):
     if arch in models.__dict__:
         return models.__dict__[arch](weights=None)
+    from torchvision.models.resnet import ResNet, Bottleneck, BasicBlock
     if arch == "resnet200":   # BASELINE.json config 5: bottleneck [3, 24, 36, 3]; not a torchvision constructor
-        from torchvision.models.resnet import ResNet, Bottleneck
         return ResNet(Bottleneck, [3, 24, 36, 3])
+    if arch.startswith("resnet:"):   # custom depth: "resnet:<basic|bottleneck>:d1,d2,d3,d4"
+        _, kind, depths = arch.split(":")
+        return ResNet(Bottleneck if kind == "bottleneck" else BasicBlock, [int(d) for d in depths.split(",")])
     raise ValueError("unknown arch %r" % arch)
 
 

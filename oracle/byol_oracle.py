@@ -41,8 +41,17 @@ ARCHS = {
 }
 
 
+def arch_spec(arch):
+    """(block kind, stage depths).  Besides the named nets, "resnet:<basic|bottleneck>:d1,d2,d3,d4" describes a
+    custom-depth ResNet (used for shallow, well-conditioned parity tests)."""
+    if arch in ARCHS:
+        return ARCHS[arch]
+    _, kind, depths = arch.split(":")
+    return kind, [int(d) for d in depths.split(",")]
+
+
 def representation_size(arch):
-    return 512 if ARCHS[arch][0] == "basic" else 2048
+    return 512 if arch_spec(arch)[0] == "basic" else 2048
 
 
 def build_reference_modules(arch, representation, projection=256, head_latent=4096, num_classes=1000):
@@ -50,7 +59,7 @@ def build_reference_modules(arch, representation, projection=256, head_latent=40
     torch.manual_seed, the initial parameters equal the reference's).  Returns an nn.Module whose
     named_parameters()/named_buffers() follow the reference's registration order."""
     import torchvision
-    kind, depths = ARCHS[arch]
+    kind, depths = arch_spec(arch)
     if arch in torchvision.models.__dict__:
         net = torchvision.models.__dict__[arch](weights=None)
     else:
@@ -127,33 +136,51 @@ class _BN(object):
         return F.batch_norm(x, rm, rv, P[prefix + ".weight"], P[prefix + ".bias"], train, self.momentum, self.eps)
 
 
-def encoder_forward(arch, P, bn, x, train, prefix="base_network", trace=None, q=_identity):
-    """torchvision ResNet (v1.5: stride on the 3x3) children[:-1] as an nn.Sequential: indices 0 conv1, 1 bn1,
-    2 relu, 3 maxpool, 4-7 layer1-4, 8 avgpool (main.py:190-193, 237)."""
-    kind, depths = ARCHS[arch]
-    conv = lambda inp, name, stride=1, pad=0: q(F.conv2d(inp, q(P[name]), None, stride, pad))
-    x = conv(q(x), prefix + ".0.weight", 2, 3)
+def block_list(arch, prefix="base_network"):
+    """[(parameter prefix, stride)] of the residual blocks in execution order."""
+    kind, depths = arch_spec(arch)
+    return [("%s.%d.%d" % (prefix, 4 + li, bi), 2 if (li > 0 and bi == 0) else 1)
+            for li, depth in enumerate(depths) for bi in range(depth)]
+
+
+def stem_forward(P, bn, x, train, prefix="base_network", q=_identity, trace=None):
+    """conv 7x7/2 -> BN -> ReLU -> maxpool 3x3/2 (torchvision resnet stem; children 0-3 of main.py:190-193)."""
+    x = q(F.conv2d(q(x), q(P[prefix + ".0.weight"]), None, 2, 3))
+    if trace is not None:
+        trace.append(("stem_conv", x.detach()))
     x = q(torch.relu(bn(x, prefix + ".1", P, train)))
-    x = F.max_pool2d(x, 3, 2, 1)
+    if trace is not None:
+        trace.append(("stem_act", x.detach()))
+    return F.max_pool2d(x, 3, 2, 1)
+
+
+def block_forward(kind, P, bn, x, p, stride, train, q=_identity):
+    """One torchvision BasicBlock / Bottleneck (v1.5: the stride sits on the 3x3)."""
+    conv = lambda inp, name, st=1, pad=0: q(F.conv2d(inp, q(P[name]), None, st, pad))
+    identity = x
+    if kind == "bottleneck":
+        out = q(torch.relu(bn(conv(x, p + ".conv1.weight"), p + ".bn1", P, train)))
+        out = q(torch.relu(bn(conv(out, p + ".conv2.weight", stride, 1), p + ".bn2", P, train)))
+        out = bn(conv(out, p + ".conv3.weight"), p + ".bn3", P, train)
+    else:
+        out = q(torch.relu(bn(conv(x, p + ".conv1.weight", stride, 1), p + ".bn1", P, train)))
+        out = bn(conv(out, p + ".conv2.weight", 1, 1), p + ".bn2", P, train)
+    if (p + ".downsample.0.weight") in P:
+        identity = bn(conv(x, p + ".downsample.0.weight", stride), p + ".downsample.1", P, train)
+    return q(torch.relu(out + identity))
+
+
+def encoder_forward(arch, P, bn, x, train, prefix="base_network", trace=None, q=_identity):
+    """torchvision ResNet children[:-1] as an nn.Sequential: indices 0 conv1, 1 bn1, 2 relu, 3 maxpool,
+    4-7 layer1-4, 8 avgpool (main.py:190-193, 237)."""
+    kind, _ = arch_spec(arch)
+    x = stem_forward(P, bn, x, train, prefix, q, trace)
     if trace is not None:
         trace.append(("pool", x.detach()))
-    for li, depth in enumerate(depths):
-        for bi in range(depth):
-            p = "%s.%d.%d" % (prefix, 4 + li, bi)
-            stride = 2 if (li > 0 and bi == 0) else 1
-            identity = x
-            if kind == "bottleneck":
-                out = q(torch.relu(bn(conv(x, p + ".conv1.weight"), p + ".bn1", P, train)))
-                out = q(torch.relu(bn(conv(out, p + ".conv2.weight", stride, 1), p + ".bn2", P, train)))
-                out = bn(conv(out, p + ".conv3.weight"), p + ".bn3", P, train)
-            else:
-                out = q(torch.relu(bn(conv(x, p + ".conv1.weight", stride, 1), p + ".bn1", P, train)))
-                out = bn(conv(out, p + ".conv2.weight", 1, 1), p + ".bn2", P, train)
-            if (p + ".downsample.0.weight") in P:
-                identity = bn(conv(x, p + ".downsample.0.weight", stride), p + ".downsample.1", P, train)
-            x = q(torch.relu(out + identity))
-            if trace is not None:
-                trace.append((p, x.detach()))
+    for p, stride in block_list(arch, prefix):
+        x = block_forward(kind, P, bn, x, p, stride, train, q)
+        if trace is not None:
+            trace.append((p, x.detach()))
     return x.mean((2, 3))  # AdaptiveAvgPool2d(1) + view(-1, C)  (main.py:237)
 
 
