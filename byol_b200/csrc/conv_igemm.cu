@@ -58,42 +58,51 @@ struct SmemLayout {
 };
 
 // ---------------------------------------------------------------------------------------------
-// fprop / dgrad kernel
+// fprop / dgrad kernel — persistent: each CTA loops over output tiles (tile = blockIdx.x + i*gridDim.x,
+// n-tile fastest so that concurrently running CTAs share the A tile through L2).  The smem operand ring and
+// the two TMEM accumulator stages run across tile boundaries, so the producers prefetch tile i+1 and the
+// tensor core works on it while the epilogue warps drain tile i.
+//   warps 0-3           : epilogue (TMEM lanes 32*w .. 32*w+31)
+//   warps 4-7 (!A_TMA)  : A-operand gather producers
+//   next warp           : MMA issuer (+ TMEM alloc / dealloc)
+//   last warp           : barrier init + TMA producer
 // ---------------------------------------------------------------------------------------------
 template <int BN, int STAGES, bool A_TMA>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(A_TMA ? 192 : 320, 2)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
-                  const ConvGemmParams p) {
+                  const ConvGemmParams p, const int num_tiles) {
   using L = SmemLayout<BN, STAGES>;
+  constexpr int MMA_WARP = A_TMA ? 4 : 8;
+  constexpr int TMA_WARP = MMA_WARP + 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smemA = smem + L::A_OFF;
   uint8_t* smemB = smem + L::B_OFF;
   uint64_t* full_bar = (uint64_t*)(smem + L::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator stage ready for the epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator stage drained
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tile_n = blockIdx.x % p.tiles_n;
-  const int tile_m = blockIdx.x / p.tiles_n;
-  const int m0 = tile_m * BM;
-  const int n0 = tile_n * BN;
   const int num_kb = p.num_kb;
 
-  if (warp == 5 && lane == 0) {
+  if (warp == TMA_WARP && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], A_TMA ? 1u : 129u);
       mbar_init(&empty_bar[s], 1u);
     }
-    mbar_init(accum_bar, 1u);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1u);
+      mbar_init(&tempty_bar[a], 4u);   // one arrival per epilogue warp
+    }
     fence_mbar_init();
     tma_prefetch_desc(&tmapB);
     if (A_TMA) tma_prefetch_desc(&tmapA);
   }
-  if (warp == 4) {
-    tmem_alloc(tmem_slot, BN);
+  if (warp == MMA_WARP) {
+    tmem_alloc(tmem_slot, 2 * BN);
     tmem_relinquish();
   }
   tc_fence_before_sync();
@@ -102,10 +111,123 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
+    // ======================= epilogue =====================================================
+    const bool do_stats = p.col_sum != nullptr;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int tile_n = tile % p.tiles_n;
+      const int m0 = (tile / p.tiles_n) * BM;
+      const int n0 = tile_n * BN;
+      const int acc = local & 1;
+      mbar_wait(&tfull_bar[acc], (uint32_t)((local >> 1) & 1));
+      tc_fence_after_sync();
+      const int m = m0 + warp * 32 + lane;
+      const bool mvalid = m < p.M;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        tmem_ld_wait();
+        if (c0 + 32 >= BN) {
+          // last TMEM read of this tile: hand the accumulator stage back to the MMA warp
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        const int nbase = n0 + c0;
+        if (nbase >= p.Ndim) continue;  // warp-uniform
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nbase + j < p.Ndim) v[j] += __ldg(p.bias + nbase + j);
+        }
+        if (p.resid != nullptr && mvalid) {
+          const bf16* rp = p.resid + (int64_t)m * p.ldc + nbase;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (nbase + j < p.Ndim) {
+              uint4 q = *reinterpret_cast<const uint4*>(rp + j);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 f = __bfloat1622float2(h[e]);
+                v[j + 2 * e] += f.x;
+                v[j + 2 * e + 1] += f.y;
+              }
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.out_fp32) {
+          if (mvalid) {
+            float* op = reinterpret_cast<float*>(p.dst) + (int64_t)m * p.ldc + nbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (nbase + j < p.Ndim)
+                *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        } else {
+          // round to bf16 first so that fused statistics describe exactly what is stored
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+          if (mvalid) {
+            bf16* op = reinterpret_cast<bf16*>(p.dst) + (int64_t)m * p.ldc + nbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (nbase + j < p.Ndim) {
+                uint4 q;
+                q.x = pack_bf16x2(v[j], v[j + 1]);
+                q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                q.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(op + j) = q;
+              }
+            }
+          }
+        }
+        if (do_stats) {
+          // per-channel sum / sum of squares over this warp's 32 rows: butterfly transpose-reduce
+          // (31 shuffles per quantity), lane j ends up holding column j; one atomic per column per warp
+          float a[32], b[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            a[j] = mvalid ? v[j] : 0.f;
+            b[j] = a[j] * a[j];
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < off; ++j) {
+              const float sa = upper ? a[j] : a[j + off];
+              const float ka = upper ? a[j + off] : a[j];
+              a[j] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
+              const float sb = upper ? b[j] : b[j + off];
+              const float kb2 = upper ? b[j + off] : b[j];
+              b[j] = kb2 + __shfl_xor_sync(0xffffffffu, sb, off);
+            }
+          }
+          if (nbase + lane < p.Ndim) {
+            atomicAdd(p.col_sum + nbase + lane, a[0]);
+            atomicAdd(p.col_sqsum + nbase + lane, b[0]);
+          }
+        }
+      }
+    }
+  } else if (!A_TMA && warp < 8) {
     // ======================= A gather producers ==========================================
-    if (!A_TMA) {
-      const int chunk = threadIdx.x & 7;   // 16-byte chunk inside the 128-byte k-row
-      const int row0 = threadIdx.x >> 3;   // rows row0 + 16*i
+    const int tid = threadIdx.x - 128;
+    const int chunk = tid & 7;   // 16-byte chunk inside the 128-byte k-row
+    const int row0 = tid >> 3;   // rows row0 + 16*i
+    int it = 0;                  // k-block iteration counter across tiles
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.tiles_n) * BM;
       int bh[8], bw[8];
       int64_t ioff[8];
 #pragma unroll
@@ -125,9 +247,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           ioff[i] = 0;
         }
       }
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         const int k0 = kb * BK + chunk * 8;
         const bool kvalid = k0 < p.Kg;
@@ -151,158 +273,71 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           cp_async16_zfill(stage_base + sw128_offset(row0 + 16 * i, chunk), g, v);
         }
         cp_async_commit();
-        if (kb >= GATHER_LAG) {
+        if (it >= GATHER_LAG) {
           cp_async_wait<GATHER_LAG>();
           fence_proxy_async_smem();
-          mbar_arrive(&full_bar[(kb - GATHER_LAG) % STAGES]);
-        }
-      }
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      for (int kb = (num_kb > GATHER_LAG ? num_kb - GATHER_LAG : 0); kb < num_kb; ++kb)
-        mbar_arrive(&full_bar[kb % STAGES]);
-    }
-
-    // ======================= epilogue =====================================================
-    mbar_wait(accum_bar, 0);
-    tc_fence_after_sync();
-    const int row = warp * 32 + lane;
-    const int m = m0 + row;
-    const bool mvalid = m < p.M;
-    const bool do_stats = p.col_sum != nullptr;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-      tmem_ld_wait();
-      const int nbase = n0 + c0;
-      if (nbase >= p.Ndim) continue;  // warp-uniform
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      if (p.bias != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (nbase + j < p.Ndim) v[j] += __ldg(p.bias + nbase + j);
-      }
-      if (p.resid != nullptr && mvalid) {
-        const bf16* rp = p.resid + (int64_t)m * p.ldc + nbase;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          if (nbase + j < p.Ndim) {
-            uint4 q = *reinterpret_cast<const uint4*>(rp + j);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float2 f = __bfloat1622float2(h[e]);
-              v[j + 2 * e] += f.x;
-              v[j + 2 * e + 1] += f.y;
-            }
-          }
-        }
-      }
-      if (p.relu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      }
-      if (p.out_fp32) {
-        if (mvalid) {
-          float* op = reinterpret_cast<float*>(p.dst) + (int64_t)m * p.ldc + nbase;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            if (nbase + j < p.Ndim)
-              *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-      } else {
-        // round to bf16 first so that fused statistics describe exactly what is stored
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
-        if (mvalid) {
-          bf16* op = reinterpret_cast<bf16*>(p.dst) + (int64_t)m * p.ldc + nbase;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (nbase + j < p.Ndim) {
-              uint4 q;
-              q.x = pack_bf16x2(v[j], v[j + 1]);
-              q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-              q.z = pack_bf16x2(v[j + 4], v[j + 5]);
-              q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(op + j) = q;
-            }
-          }
-        }
-      }
-      if (do_stats) {
-        // per-channel sum / sum of squares over this warp's 32 rows: butterfly transpose-reduce
-        // (31 shuffles per quantity), lane j ends up holding column j; one atomic per column per warp
-        float a[32], b[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          a[j] = mvalid ? v[j] : 0.f;
-          b[j] = a[j] * a[j];
-        }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-          const bool upper = (lane & off) != 0;
-#pragma unroll
-          for (int j = 0; j < off; ++j) {
-            const float sa = upper ? a[j] : a[j + off];
-            const float ka = upper ? a[j + off] : a[j];
-            a[j] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
-            const float sb = upper ? b[j] : b[j + off];
-            const float kb2 = upper ? b[j + off] : b[j];
-            b[j] = kb2 + __shfl_xor_sync(0xffffffffu, sb, off);
-          }
-        }
-        if (nbase + lane < p.Ndim) {
-          atomicAdd(p.col_sum + nbase + lane, a[0]);
-          atomicAdd(p.col_sqsum + nbase + lane, b[0]);
+          mbar_arrive(&full_bar[(it - GATHER_LAG) % STAGES]);
         }
       }
     }
-    tc_fence_before_sync();
-  } else if (warp == 4) {
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    for (int j = (it > GATHER_LAG ? it - GATHER_LAG : 0); j < it; ++j) mbar_arrive(&full_bar[j % STAGES]);
+  } else if (warp == MMA_WARP) {
     // ======================= MMA issuer ===================================================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(1u, BM, BN, 0u, 0u);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int it = 0, local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        mbar_wait(&tempty_bar[acc], (uint32_t)(((local >> 1) & 1) ^ 1));
         tc_fence_after_sync();
-        const uint64_t adesc = make_smem_desc_sw128(smem_u32(smemA + s * A_STAGE_BYTES), 16, 1024);
-        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smemB + s * L::B_STAGE_BYTES), 16, 1024);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after_sync();
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(smemA + s * A_STAGE_BYTES), 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smemB + s * L::B_STAGE_BYTES), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                    (uint32_t)((kb | k) != 0));
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                      (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(&empty_bar[s]);
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit(&tfull_bar[acc]);
       }
-      umma_commit(accum_bar);
     }
     __syncwarp();
-  } else {
+  } else if (warp == TMA_WARP) {
     // ======================= TMA producer =================================================
     if (lane == 0) {
       constexpr uint32_t tx = (uint32_t)L::B_STAGE_BYTES + (A_TMA ? (uint32_t)A_STAGE_BYTES : 0u);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], tx);
-        tma_load_2d(smem_u32(smemB + s * L::B_STAGE_BYTES), &tmapB, &full_bar[s], kb * BK, n0);
-        if (A_TMA) tma_load_2d(smem_u32(smemA + s * A_STAGE_BYTES), &tmapA, &full_bar[s], kb * BK, m0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.tiles_n) * BN;
+        const int m0 = (tile / p.tiles_n) * BM;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], tx);
+          tma_load_2d(smem_u32(smemB + s * L::B_STAGE_BYTES), &tmapB, &full_bar[s], kb * BK, n0);
+          if (A_TMA) tma_load_2d(smem_u32(smemA + s * A_STAGE_BYTES), &tmapA, &full_bar[s], kb * BK, m0);
+        }
       }
     }
     __syncwarp();
   }
 
+  tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -324,6 +359,7 @@ struct WgradParams {
   int Cout, Cin_real;
   int tiles_co, tiles_ci;
   int splits, kb_per_split, num_kb_total;
+  int fold_kw;       // 1: C == 8 and the KW taps are folded into the channel dimension (stem): B column = kw*8 + c
 };
 
 static constexpr int WG_KROWS = 64;  // pixels per k-block
@@ -351,7 +387,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   const int tile_co = bid % p.tiles_co;  bid /= p.tiles_co;
   const int split = bid % p.splits;      bid /= p.splits;
   const int tap = bid;
-  const int kh = tap / p.KW, kw = tap - kh * p.KW;
+  // folded (stem) mode: one CTA group per kh, the kw taps live in the B columns
+  const int kh = p.fold_kw ? tap : tap / p.KW;
+  const int kw = p.fold_kw ? 0 : tap - kh * p.KW;
+  const int kh_tap = kh;
   const int co0 = tile_co * 128;
   const int ci0 = tile_ci * BN;
   const int kb_begin = split * p.kb_per_split;
@@ -380,36 +419,43 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 
   if (warp < 4) {
     if (!B_TMA) {
-      // gather: 64 pixel rows x (NCH*8) 16-byte chunks per stage, 128 threads
+      // gather: 64 pixel rows x (NCH*8) 16-byte chunks per stage, 128 threads.  Thread t owns chunk column
+      // (t % CHUNKS) of rows r0 + ROW_STEP*i; pixel coordinates are advanced incrementally (no per-element division).
       constexpr int CHUNKS = NCH * 8;
       constexpr int PER_THREAD = WG_KROWS * CHUNKS / 128;
+      constexpr int ROW_STEP = 128 / CHUNKS;
+      const int chunk = threadIdx.x % CHUNKS;
+      const int r0 = threadIdx.x / CHUNKS;
+      const int ch64 = chunk >> 3, c16 = chunk & 7;
+      const int ci = p.fold_kw ? 0 : ci0 + chunk * 8;
+      const int kw_eff = p.fold_kw ? chunk : kw;          // folded: the chunk index is the kw tap
+      const bool cvalid = p.fold_kw ? (chunk < p.KW) : (ci < p.C);
+      const int dh = kh - p.pad, dw = kw_eff - p.pad;
       for (int it = 0; it < nkb; ++it) {
         const int kb = kb_begin + it;
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        const uint32_t stage_base = smem_u32(smemB + s * B_STAGE);
+        const uint32_t stage_base = smem_u32(smemB + s * B_STAGE) + ch64 * (WG_KROWS * 128);
+        int m = kb * WG_KROWS + r0;
+        int ow = m % p.Wo;
+        int t = m / p.Wo;
+        int oh = t % p.Ho;
+        int n = t / p.Ho;
 #pragma unroll
         for (int i = 0; i < PER_THREAD; ++i) {
-          const int idx = threadIdx.x + 128 * i;
-          const int chunk = idx % CHUNKS;
-          const int r = idx / CHUNKS;
-          const int m = kb * WG_KROWS + r;
-          const int ci = ci0 + chunk * 8;
-          bool v = m < p.M && ci < p.C;
-          const bf16* g = p.src;
-          if (v) {
-            int ow = m % p.Wo;
-            int t = m / p.Wo;
-            int oh = t % p.Ho;
-            int n = t / p.Ho;
-            int sh = oh * p.stride - p.pad + kh;
-            int sw = ow * p.stride - p.pad + kw;
-            v = sh >= 0 && sw >= 0 && sh < p.Hs && sw < p.Ws;
-            if (v) g = p.src + (((int64_t)n * p.Hs + sh) * p.Ws + sw) * p.C + ci;
+          const int r = r0 + ROW_STEP * i;
+          const int sh = oh * p.stride + dh;
+          const int sw = ow * p.stride + dw;
+          const bool v = cvalid && m < p.M && sh >= 0 && sw >= 0 && sh < p.Hs && sw < p.Ws;
+          const bf16* g = v ? p.src + (((int64_t)n * p.Hs + sh) * p.Ws + sw) * p.C + ci : p.src;
+          cp_async16_zfill(stage_base + sw128_offset(r, c16), g, v);
+          m += ROW_STEP;
+          ow += ROW_STEP;
+          while (ow >= p.Wo) {
+            ow -= p.Wo;
+            if (++oh == p.Ho) { oh = 0; ++n; }
           }
-          const int ch64 = chunk >> 3, c16 = chunk & 7;
-          cp_async16_zfill(stage_base + ch64 * (WG_KROWS * 128) + sw128_offset(r, c16), g, v);
         }
         cp_async_commit();
         if (it >= GATHER_LAG) {
@@ -434,11 +480,21 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
       tmem_ld_wait();
       if (covalid) {
-        float* gp = p.dw + ((int64_t)co * p.Cin_real) * taps + tap;
+        if (p.fold_kw) {
+          // column = kw*8 + ci ; tap index here is kh
+          float* gp = p.dw + ((int64_t)co * p.Cin_real) * taps + kh_tap * p.KW;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          int ci = ci0 + c0 + j;
-          if (ci < p.Cin_real) atomicAdd(gp + (int64_t)ci * taps, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; ++j) {
+            const int col = c0 + j, kwj = col >> 3, cj = col & 7;
+            if (kwj < p.KW && cj < p.Cin_real) atomicAdd(gp + (int64_t)cj * taps + kwj, __uint_as_float(r[j]));
+          }
+        } else {
+          float* gp = p.dw + ((int64_t)co * p.Cin_real) * taps + tap;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            int ci = ci0 + c0 + j;
+            if (ci < p.Cin_real) atomicAdd(gp + (int64_t)ci * taps, __uint_as_float(r[j]));
+          }
         }
       }
     }
@@ -536,6 +592,16 @@ static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64
   return 0;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int BN, int STAGES, bool A_TMA>
 static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const ConvGemmParams& p, int tiles_m,
                         cudaStream_t stream) {
@@ -550,7 +616,10 @@ static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const Conv
     }
     attr_set = true;
   }
-  kern<<<tiles_m * p.tiles_n, 192, L::TOTAL, stream>>>(ta, tb, p);
+  const int num_tiles = tiles_m * p.tiles_n;
+  int grid = 2 * sm_count();           // persistent: two CTAs per SM (smem and TMEM sized for it)
+  if (grid > num_tiles) grid = num_tiles;
+  kern<<<grid, A_TMA ? 192 : 320, L::TOTAL, stream>>>(ta, tb, p, num_tiles);
   return check_launch("conv_igemm_kernel");
 }
 
@@ -653,10 +722,11 @@ extern "C" int byol_conv_wgrad(const void* src, const void* dy, float* dw, int N
   p.Cout = Cout;
   p.Cin_real = Cin_real;
   const int BN = (C > 128) ? 256 : (C > 64 ? 128 : 64);
+  p.fold_kw = (C == 8 && KW <= 8 && KW > 1) ? 1 : 0;
   p.tiles_co = (Cout + 127) / 128;
   p.tiles_ci = (C + BN - 1) / BN;
   p.num_kb_total = (p.M + WG_KROWS - 1) / WG_KROWS;
-  const int taps = KH * KW;
+  const int taps = p.fold_kw ? KH : KH * KW;
   const int base_ctas = p.tiles_co * p.tiles_ci * taps;
   int splits = (148 * 4 + base_ctas - 1) / base_ctas;       // aim for ~4 waves of CTAs
   int max_splits = (p.num_kb_total + 7) / 8;                // at least 8 k-blocks (512 pixels) per CTA
