@@ -54,7 +54,10 @@ struct SmemLayout {
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
   static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // +1024 alignment slack
+  // 4 epilogue warps x [32 rows][64 B]; the TMA 64-byte swizzle pattern repeats every 512 B, so every
+  // warp tile must start on a 512-byte boundary (here: 1024-aligned base + multiples of 2048)
+  static constexpr int STAGE_OUT_OFF = BAR_OFF + 1024;
+  static constexpr int TOTAL = STAGE_OUT_OFF + 4 * 2048 + 1024;  // +1024 alignment slack
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -70,7 +73,7 @@ struct SmemLayout {
 template <int BN, int STAGES, bool A_TMA>
 __global__ void __launch_bounds__(A_TMA ? 192 : 320, 2)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
-                  const ConvGemmParams p, const int num_tiles) {
+                  const __grid_constant__ CUtensorMap tmapC, const ConvGemmParams p, const int num_tiles) {
   using L = SmemLayout<BN, STAGES>;
   constexpr int MMA_WARP = A_TMA ? 4 : 8;
   constexpr int TMA_WARP = MMA_WARP + 1;
@@ -83,6 +86,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator stage ready for the epilogue
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator stage drained
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+  uint8_t* stage_out = smem + L::STAGE_OUT_OFF;   // 1024-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -100,6 +104,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     fence_mbar_init();
     tma_prefetch_desc(&tmapB);
     if (A_TMA) tma_prefetch_desc(&tmapA);
+    if (!p.out_fp32) tma_prefetch_desc(&tmapC);
   }
   if (warp == MMA_WARP) {
     tmem_alloc(tmem_slot, 2 * BN);
@@ -112,23 +117,50 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 
   if (warp < 4) {
     // ======================= epilogue =====================================================
+    // Per 32-column chunk: TMEM -> registers -> (bias / residual / ReLU) -> bf16 -> this warp's swizzled
+    // smem staging tile [32 rows][64 B] -> one TMA store (no LSU global stores).  While the TMA engine reads the
+    // staging tile, the warp sums its 32 rows per column from the same tile (lane = column) for the fused
+    // BatchNorm statistics; the sums stay in registers across all tiles of this CTA that share a column block.
     const bool do_stats = p.col_sum != nullptr;
+    const uint32_t stage_base = smem_u32(stage_out + warp * 2048);
+    const uint8_t* stage_ptr = stage_out + warp * 2048;
+    float csum[BN / 32], csq[BN / 32];
+#pragma unroll
+    for (int i = 0; i < BN / 32; ++i) { csum[i] = 0.f; csq[i] = 0.f; }
     int local = 0;
+    int stat_n0 = -1;   // column offset the register accumulators currently belong to
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int tile_n = tile % p.tiles_n;
       const int m0 = (tile / p.tiles_n) * BM;
       const int n0 = tile_n * BN;
+      if (do_stats && stat_n0 != n0) {
+        if (stat_n0 >= 0) {
+#pragma unroll
+          for (int i = 0; i < BN / 32; ++i) {
+            if (stat_n0 + i * 32 + lane < p.Ndim) {
+              atomicAdd(p.col_sum + stat_n0 + i * 32 + lane, csum[i]);
+              atomicAdd(p.col_sqsum + stat_n0 + i * 32 + lane, csq[i]);
+            }
+            csum[i] = 0.f; csq[i] = 0.f;
+          }
+        }
+        stat_n0 = n0;
+      }
       const int acc = local & 1;
       mbar_wait(&tfull_bar[acc], (uint32_t)((local >> 1) & 1));
       tc_fence_after_sync();
-      const int m = m0 + warp * 32 + lane;
+      const int mrow0 = m0 + warp * 32;
+      const int m = mrow0 + lane;
       const bool mvalid = m < p.M;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      int rows_valid = p.M - mrow0;
+      rows_valid = rows_valid < 0 ? 0 : (rows_valid > 32 ? 32 : rows_valid);
+#pragma unroll
+      for (int ci = 0; ci < BN / 32; ++ci) {
+        const int c0 = ci * 32;
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), r);
         tmem_ld_wait();
-        if (c0 + 32 >= BN) {
+        if (ci == BN / 32 - 1) {
           // last TMEM read of this tile: hand the accumulator stage back to the MMA warp
           tc_fence_before_sync();
           __syncwarp();
@@ -173,53 +205,57 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                 *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
         } else {
-          // round to bf16 first so that fused statistics describe exactly what is stored
+          // stage this warp's [32 rows][32 cols] bf16 block: row = lane, 16-byte chunk j at (j ^ ((row >> 1) & 3))
+          // (= the TMA 64-byte swizzle), which also spreads the 32 row-writes over all banks
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
-          if (mvalid) {
-            bf16* op = reinterpret_cast<bf16*>(p.dst) + (int64_t)m * p.ldc + nbase;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (nbase + j < p.Ndim) {
-                uint4 q;
-                q.x = pack_bf16x2(v[j], v[j + 1]);
-                q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                q.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(op + j) = q;
+          for (int j = 0; j < 4; ++j) {
+            uint4 q;
+            q.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+            q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+            q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            const uint32_t off = (uint32_t)lane * 64u + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_base + off), "r"(q.x), "r"(q.y),
+                         "r"(q.z), "r"(q.w)
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmapC, stage_base, nbase, mrow0);   // rows >= M and columns >= Ndim are clipped by TMA
+            tma_store_commit();
+          }
+          if (do_stats) {
+            // lane = column: sum the stored (bf16-rounded) values of this warp's valid rows
+            float s1 = 0.f, s2 = 0.f;
+            const int jc = lane >> 3, e2 = (lane & 7) * 2;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              if (rr < rows_valid) {
+                const bf16 hv = *reinterpret_cast<const bf16*>(stage_ptr + rr * 64 + ((jc ^ ((rr >> 1) & 3)) << 4) + e2);
+                const float x = __bfloat162float(hv);
+                s1 += x;
+                s2 += x * x;
               }
             }
+            csum[ci] += s1;
+            csq[ci] += s2;
           }
-        }
-        if (do_stats) {
-          // per-channel sum / sum of squares over this warp's 32 rows: butterfly transpose-reduce
-          // (31 shuffles per quantity), lane j ends up holding column j; one atomic per column per warp
-          float a[32], b[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            a[j] = mvalid ? v[j] : 0.f;
-            b[j] = a[j] * a[j];
-          }
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool upper = (lane & off) != 0;
-#pragma unroll
-            for (int j = 0; j < off; ++j) {
-              const float sa = upper ? a[j] : a[j + off];
-              const float ka = upper ? a[j + off] : a[j];
-              a[j] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
-              const float sb = upper ? b[j] : b[j + off];
-              const float kb2 = upper ? b[j + off] : b[j];
-              b[j] = kb2 + __shfl_xor_sync(0xffffffffu, sb, off);
-            }
-          }
-          if (nbase + lane < p.Ndim) {
-            atomicAdd(p.col_sum + nbase + lane, a[0]);
-            atomicAdd(p.col_sqsum + nbase + lane, b[0]);
-          }
+          if (lane == 0) tma_store_wait_read();   // the staging tile may be overwritten after this
+          __syncwarp();
         }
       }
     }
+    if (do_stats && stat_n0 >= 0) {
+#pragma unroll
+      for (int i = 0; i < BN / 32; ++i) {
+        if (stat_n0 + i * 32 + lane < p.Ndim) {
+          atomicAdd(p.col_sum + stat_n0 + i * 32 + lane, csum[i]);
+          atomicAdd(p.col_sqsum + stat_n0 + i * 32 + lane, csq[i]);
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();   // global writes complete before the kernel exits
   } else if (!A_TMA && warp < 8) {
     // ======================= A gather producers ==========================================
     const int tid = threadIdx.x - 128;
@@ -572,18 +608,20 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map: `rows` x `cols` (cols contiguous), row pitch `ld` elements, box = box_rows x 64 cols
+// 2-D bf16 tensor map: `rows` x `cols` (cols contiguous), row pitch `ld` elements.
+// box = box_rows x box_cols with box_cols = 64 (128-byte swizzle, operand loads) or 32 (64-byte swizzle, output stores)
 static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                        uint32_t box_rows) {
+                        uint32_t box_rows, uint32_t box_cols = 64u) {
   PFN_encodeTiled fn = get_encode_fn();
   if (fn == nullptr) return -1;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * sizeof(bf16)};
-  cuuint32_t box[2] = {64u, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  box_cols == 64u ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu ld=%llu box_rows=%u base=%p", (int)r,
                    (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, base);
@@ -603,8 +641,8 @@ static int sm_count() {
 }
 
 template <int BN, int STAGES, bool A_TMA>
-static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const ConvGemmParams& p, int tiles_m,
-                        cudaStream_t stream) {
+static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                        const ConvGemmParams& p, int tiles_m, cudaStream_t stream) {
   using L = SmemLayout<BN, STAGES>;
   auto kern = conv_igemm_kernel<BN, STAGES, A_TMA>;
   static bool attr_set = false;
@@ -619,7 +657,7 @@ static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const Conv
   const int num_tiles = tiles_m * p.tiles_n;
   int grid = 2 * sm_count();           // persistent: two CTAs per SM (smem and TMEM sized for it)
   if (grid > num_tiles) grid = num_tiles;
-  kern<<<grid, A_TMA ? 192 : 320, L::TOTAL, stream>>>(ta, tb, p, num_tiles);
+  kern<<<grid, A_TMA ? 192 : 320, L::TOTAL, stream>>>(ta, tb, tc, p, num_tiles);
   return check_launch("conv_igemm_kernel");
 }
 
@@ -668,20 +706,25 @@ extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const
   const int tiles_m = (p.M + BM - 1) / BM;
   const bool a_tma = !force_gather && KH == 1 && KW == 1 && stride == 1 && pad == 0;
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc;
   memset(&ta, 0, sizeof(ta));
   if (make_tmap_2d(&tb, wt, (uint64_t)Ndim, (uint64_t)p.Kg, (uint64_t)ldw, (uint32_t)BN) != 0) return -3;
+  if (!out_fp32) {
+    if (make_tmap_2d(&tc, dst, (uint64_t)p.M, (uint64_t)Ndim, (uint64_t)ldc, 32u, 32u) != 0) return -3;
+  } else {
+    tc = tb;
+  }
   if (a_tma) {
     if (make_tmap_2d(&ta, src, (uint64_t)p.M, (uint64_t)C, (uint64_t)C, (uint32_t)BM) != 0) return -3;
   } else {
     ta = tb;
   }
   if (BN == 128) {
-    return a_tma ? launch_igemm<128, 3, true>(ta, tb, p, tiles_m, stream)
-                 : launch_igemm<128, 3, false>(ta, tb, p, tiles_m, stream);
+    return a_tma ? launch_igemm<128, 3, true>(ta, tb, tc, p, tiles_m, stream)
+                 : launch_igemm<128, 3, false>(ta, tb, tc, p, tiles_m, stream);
   }
-  return a_tma ? launch_igemm<64, 4, true>(ta, tb, p, tiles_m, stream)
-               : launch_igemm<64, 4, false>(ta, tb, p, tiles_m, stream);
+  return a_tma ? launch_igemm<64, 4, true>(ta, tb, tc, p, tiles_m, stream)
+               : launch_igemm<64, 4, false>(ta, tb, tc, p, tiles_m, stream);
 }
 
 template <int BN, bool B_TMA>
