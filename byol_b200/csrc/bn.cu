@@ -161,6 +161,99 @@ __global__ void bn_apply_kernel(const bf16* __restrict__ x, const float* __restr
   }
 }
 
+// Same as bn_apply_kernel, for launches where (gridDim.x * blockDim.x) % (C/8) == 0: every thread then stays on
+// ONE 8-channel group for its whole grid-stride loop and keeps the per-channel coefficients in registers
+// (the generic kernel re-loads them per vector, which makes it LSU-bound rather than HBM-bound).
+template <bool RESID, bool RAFFINE>
+__global__ void __launch_bounds__(256)
+bn_apply_fixed_kernel(const bf16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                      const bf16* __restrict__ resid, const float* __restrict__ rscale,
+                      const float* __restrict__ rshift, bf16* __restrict__ y, int64_t nvec, int C, int relu) {
+  const int groups = C >> 3;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int g = (int)(tid % groups);
+  float sc[8], sh[8], rs[8], rb[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sc[e] = scale[g * 8 + e];
+    sh[e] = shift[g * 8 + e];
+    rs[e] = RAFFINE ? rscale[g * 8 + e] : 1.f;
+    rb[e] = RAFFINE ? rshift[g * 8 + e] : 0.f;
+  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < nvec; i += stride) {
+    float xv[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), xv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = xv[e] * sc[e] + sh[e];
+    if (RESID) {
+      float rv[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(resid) + i), rv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] += RAFFINE ? (rv[e] * rs[e] + rb[e]) : rv[e];
+    }
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+    }
+    reinterpret_cast<uint4*>(y)[i] = pack8(o);
+  }
+}
+
+// dy = A*dz + B*x + Cc with per-channel A = gamma*invstd, B = -gamma*invstd^2*s2/n,
+// Cc = gamma*invstd*(mean*invstd*s2/n - s1/n); same thread <-> channel-group pinning as bn_apply_fixed_kernel.
+template <int MASK>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_fixed_kernel(const bf16* __restrict__ g, const bf16* __restrict__ x, const bf16* __restrict__ act,
+                          const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                          const float* __restrict__ gamma, const float* __restrict__ s1,
+                          const float* __restrict__ s2, float inv_count, bf16* __restrict__ dy,
+                          bf16* __restrict__ dz_out, int64_t nvec, int C, const float* __restrict__ s1_local,
+                          const float* __restrict__ s2_local, float* __restrict__ dgamma,
+                          float* __restrict__ dbeta) {
+  const int groups = C >> 3;
+  if (blockIdx.x == 0 && dgamma != nullptr) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      dgamma[c] += s2_local[c];
+      dbeta[c] += s1_local[c];
+    }
+  }
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int gi = (int)(tid % groups);
+  float A[8], B[8], Cc[8], sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = gi * 8 + e;
+    const float is = invstd[c], mu = mean[c], ga = gamma[c];
+    const float m1 = s1[c] * inv_count, m2 = s2[c] * inv_count;
+    A[e] = ga * is;
+    B[e] = -ga * is * is * m2;
+    Cc[e] = ga * is * (mu * is * m2 - m1);
+    sc[e] = MASK == 1 ? scale[c] : 0.f;
+    sh[e] = MASK == 1 ? shift[c] : 0.f;
+  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < nvec; i += stride) {
+    float gv[8], xv[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(g) + i), gv);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), xv);
+    if (MASK == 2) {
+      float av[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(act) + i), av);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gv[e] = av[e] > 0.f ? gv[e] : 0.f;
+    } else if (MASK == 1) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gv[e] = (xv[e] * sc[e] + sh[e]) > 0.f ? gv[e] : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = A[e] * gv[e] + (B[e] * xv[e] + Cc[e]);
+    reinterpret_cast<uint4*>(dy)[i] = pack8(o);
+    if (dz_out != nullptr) reinterpret_cast<uint4*>(dz_out)[i] = pack8(gv);
+  }
+}
+
 // mask_mode: 0 = none (dz = g), 1 = ReLU mask recomputed from x (x*scale+shift > 0), 2 = mask from act > 0
 template <int MASK>
 __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ x,
@@ -282,6 +375,18 @@ __global__ void col_sum_kernel(const T* __restrict__ x, float* __restrict__ out,
   atomicAdd(out + c, s);
 }
 
+// grid for the "fixed channel group" elementwise kernels: (grid*256) % groups == 0, or 0 if impossible
+static inline int fixed_grid(int64_t nvec, int groups) {
+  int unit = groups > 256 ? groups / 256 : 1;          // blocks per channel period
+  if (groups > 256 ? (groups % 256 != 0) : (256 % groups != 0)) return 0;
+  int64_t b = (nvec + 255) / 256;
+  int64_t cap = 148 * 8;
+  if (b > cap) b = cap;
+  b = (b + unit - 1) / unit * unit;
+  if (b < unit) b = unit;
+  return (int)b;
+}
+
 static inline int grid_for(int64_t n, int block, int max_blocks = 148 * 16) {
   int64_t b = (n + block - 1) / block;
   if (b > max_blocks) b = max_blocks;
@@ -328,6 +433,17 @@ extern "C" int byol_bn_apply(const void* x, const float* scale, const float* shi
                              int relu, cudaStream_t stream) {
   BYOL_CHECK_ARG(x && scale && shift && (y || y_f32) && M > 0 && C % 8 == 0, "byol_bn_apply: bad args");
   const int64_t nvec = (int64_t)M * C / 8;
+  const int fg = (y != nullptr && y_f32 == nullptr) ? fixed_grid(nvec, C / 8) : 0;
+  if (fg > 0) {
+    const bf16 *xp = (const bf16*)x, *rp = (const bf16*)resid;
+    if (resid == nullptr)
+      bn_apply_fixed_kernel<false, false><<<fg, 256, 0, stream>>>(xp, scale, shift, rp, rscale, rshift, (bf16*)y, nvec, C, relu);
+    else if (rscale == nullptr)
+      bn_apply_fixed_kernel<true, false><<<fg, 256, 0, stream>>>(xp, scale, shift, rp, rscale, rshift, (bf16*)y, nvec, C, relu);
+    else
+      bn_apply_fixed_kernel<true, true><<<fg, 256, 0, stream>>>(xp, scale, shift, rp, rscale, rshift, (bf16*)y, nvec, C, relu);
+    return check_launch("bn_apply_fixed_kernel");
+  }
   bn_apply_kernel<<<grid_for(nvec, 256), 256, 0, stream>>>((const bf16*)x, scale, shift, (const bf16*)resid, rscale,
                                                            rshift, (bf16*)y, y_f32, nvec, C, relu);
   return check_launch("bn_apply_kernel");
@@ -364,6 +480,16 @@ extern "C" int byol_bn_bwd_apply(const void* g, const void* x, const void* act, 
   const int64_t nvec = (int64_t)M * C / 8;
   const float inv_count = (float)(1.0 / count);
   const bf16 *gp = (const bf16*)g, *xp = (const bf16*)x, *ap = (const bf16*)act;
+  const int fg = fixed_grid(nvec, C / 8);
+  if (fg > 0) {
+    if (mask_mode == 0)
+      bn_bwd_apply_fixed_kernel<0><<<fg, 256, 0, stream>>>(gp, xp, ap, scale, shift, mean, invstd, gamma, s12, s12 + C, inv_count, (bf16*)dy, (bf16*)dz_out, nvec, C, s12_local, s12_local + C, dgamma, dbeta);
+    else if (mask_mode == 1)
+      bn_bwd_apply_fixed_kernel<1><<<fg, 256, 0, stream>>>(gp, xp, ap, scale, shift, mean, invstd, gamma, s12, s12 + C, inv_count, (bf16*)dy, (bf16*)dz_out, nvec, C, s12_local, s12_local + C, dgamma, dbeta);
+    else
+      bn_bwd_apply_fixed_kernel<2><<<fg, 256, 0, stream>>>(gp, xp, ap, scale, shift, mean, invstd, gamma, s12, s12 + C, inv_count, (bf16*)dy, (bf16*)dz_out, nvec, C, s12_local, s12_local + C, dgamma, dbeta);
+    return check_launch("bn_bwd_apply_fixed_kernel");
+  }
   const int grid = grid_for(nvec, 256);
   if (mask_mode == 0)
     bn_bwd_apply_kernel<0><<<grid, 256, 0, stream>>>(gp, xp, ap, scale, shift, mean, invstd, gamma, s12, s12 + C, inv_count, (bf16*)dy, (bf16*)dz_out, nvec, C, s12_local, s12_local + C, dgamma, dbeta);

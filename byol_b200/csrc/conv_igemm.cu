@@ -396,6 +396,7 @@ struct WgradParams {
   int tiles_co, tiles_ci;
   int splits, kb_per_split, num_kb_total;
   int fold_kw;       // 1: C == 8 and the KW taps are folded into the channel dimension (stem): B column = kw*8 + c
+  int vec4;          // 1: 1x1 conv with 16-byte aligned gradient rows: accumulate with red.global.add.v4.f32
 };
 
 static constexpr int WG_KROWS = 64;  // pixels per k-block
@@ -523,6 +524,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           for (int j = 0; j < 32; ++j) {
             const int col = c0 + j, kwj = col >> 3, cj = col & 7;
             if (kwj < p.KW && cj < p.Cin_real) atomicAdd(gp + (int64_t)cj * taps + kwj, __uint_as_float(r[j]));
+          }
+        } else if (p.vec4) {
+          // 1x1: the 32 columns are contiguous in memory -> 8 vector reductions instead of 32 scalar ones
+          float* gp = p.dw + (int64_t)co * p.Cin_real + ci0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (ci0 + c0 + j < p.Cin_real)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gp + j), "f"(__uint_as_float(r[j])),
+                           "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
+                           "f"(__uint_as_float(r[j + 3]))
+                           : "memory");
           }
         } else {
           float* gp = p.dw + ((int64_t)co * p.Cin_real) * taps + tap;
@@ -771,7 +783,11 @@ extern "C" int byol_conv_wgrad(const void* src, const void* dy, float* dw, int N
   p.num_kb_total = (p.M + WG_KROWS - 1) / WG_KROWS;
   const int taps = p.fold_kw ? KH : KH * KW;
   const int base_ctas = p.tiles_co * p.tiles_ci * taps;
-  int splits = (148 * 4 + base_ctas - 1) / base_ctas;       // aim for ~4 waves of CTAs
+  // The epilogue adds 128 x BN fp32 values per CTA to the gradient with L2 reductions, so the split count trades
+  // parallelism against reduction traffic: aim for one resident wave (2 CTAs/SM fit only for BN = 64).
+  p.vec4 = (taps == 1 && !p.fold_kw && Cin_real % 4 == 0 && ((uintptr_t)dw % 16 == 0)) ? 1 : 0;
+  const int target_ctas = sm_count() * (BN == 64 ? 2 : 1);
+  int splits = (target_ctas + base_ctas - 1) / base_ctas;
   int max_splits = (p.num_kb_total + 7) / 8;                // at least 8 k-blocks (512 pixels) per CTA
   if (max_splits < 1) max_splits = 1;
   if (splits > max_splits) splits = max_splits;
