@@ -18,10 +18,9 @@ Data layout: activations NHWC bf16; conv outputs are stored raw ("y") and normal
 materialised by a fused BN-apply(+residual)+ReLU kernel; BN statistics come from the conv epilogue.
 """
 import torch
-import torch.distributed as dist
 import torch.nn as nn
 
-from . import ops
+from . import comm, ops
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -190,7 +189,7 @@ class Engine(object):
         self.ready = True
 
     def world(self):
-        return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        return comm.world_size()
 
     def prep_weights(self, flat, wset, want_dgrad):
         for u in self.units:
@@ -221,7 +220,7 @@ class Engine(object):
             rows = ys[0].numel() // C
             count = rows
             if self.sync and self.world() > 1:
-                dist.all_reduce(stats)
+                comm.allreduce_sum_(stats)
                 count = rows * self.world()
             for i, (flat, _, _) in enumerate(lanes):
                 ops.bn_finalize(stats[i * 2 * C:(i + 1) * 2 * C], count, flat[u.g_off:u.g_off + C],
@@ -333,7 +332,7 @@ class Engine(object):
         count, local = rows, None
         if self.sync and self.world() > 1:
             local = s12.clone()
-            dist.all_reduce(s12)
+            comm.allreduce_sum_(s12)
             count = rows * self.world()
         gamma = self.theta[u.g_off:u.g_off + C]
         dys, dzs = [], []
@@ -470,5 +469,4 @@ class Engine(object):
 
     def _finish_backward(self):
         self._bwd_cb_queued = False
-        if self.world() > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.AVG)
+        comm.allreduce_mean_(self.grad)

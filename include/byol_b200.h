@@ -1,0 +1,107 @@
+/* byol_b200.h — C ABI of libbyol_b200.so: the sm_100a kernels behind the BYOL training-step hot path.
+ *
+ * The reference (jramapuram/BYOL) is pure Python and has no FFI / operator registry of its own; its hot path
+ * reaches cuDNN / cuBLAS / ATen / NCCL through torch.  This header is therefore the boundary a maintainer binds
+ * from Python (ctypes stub in byol_b200/_lib.py): plain pointers and sizes, one CUDA stream,
+ * no torch types, no allocation, no implicit synchronisation, no global mutable state.
+ *
+ * Conventions
+ *   - every function returns 0 on success, < 0 on error; byol_last_error() gives the thread-local message
+ *   - all pointers are device pointers unless stated otherwise; `stream` is the caller's cudaStream_t
+ *   - activations are NHWC bf16 with the channel count padded to a multiple of 8; "[M, C]" means M = N*H*W rows
+ *   - fp32 parameter / gradient tensors use the reference's layouts ([Cout, Cin, KH, KW], [out, in], [C])
+ *   - launches are asynchronous; errors detected at launch time are reported, device faults surface at the
+ *     caller's next synchronisation
+ *
+ * Reference lines cited below are relative to /root/reference (jramapuram/BYOL @ 5ea487e).
+ */
+#ifndef BYOL_B200_H
+#define BYOL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* byol_stream_t; /* == cudaStream_t */
+
+const char* byol_last_error(void);
+int byol_abi_version(void);
+int byol_device_sm_count(void);
+
+/* ---- tensor-core convolution / linear: replaces the cuDNN conv fwd/dgrad and cuBLAS Linear calls under
+ *      main.py:229-240 (BYOL.prediction -> base_network, head, predictor) and main.py:250-252 (classifier) ----
+ * out[M = Nimg*Ho*Wo, Ndim] = gather(src) x Wt^T (+bias) (+resid) (relu); optional fused per-column
+ * sum / sum-of-squares of the stored values (BatchNorm statistics).
+ *   mode 0 (fprop): src = x [Nimg,Hs,Ws,C], src coordinate = o*stride - pad + k
+ *   mode 1 (dgrad): src = dY [Nimg,Hs,Ws,C=Cout], (Ho,Wo) = spatial size of dX, coordinate = (o + pad - k)/stride
+ * wt: bf16 [Ndim, ldw] K-major with k = (kh*KW + kw)*C + c (made by byol_prep_weight). */
+int byol_conv_igemm(const void* src, const void* wt, void* dst, const void* resid, const float* bias,
+                    float* col_sum, float* col_sqsum, int Nimg, int Hs, int Ws, int C, int Ho, int Wo, int Ndim,
+                    int KH, int KW, int stride, int pad, int mode, int ldw, int ldc, int out_fp32, int relu,
+                    int force_gather, byol_stream_t stream);
+
+/* dW[Cout][Cin_real][KH][KW] (fp32, accumulated) += dY^T x im2col(x): replaces cuDNN wgrad / cuBLAS in the
+ * autograd of main.py:617 (loss.backward()). */
+int byol_conv_wgrad(const void* src, const void* dy, float* dw, int Nimg, int Hs, int Ws, int C, int Cin_real,
+                    int Ho, int Wo, int Cout, int KH, int KW, int stride, int pad, int force_gather,
+                    byol_stream_t stream);
+
+/* ---- BatchNorm (train / eval, optionally cross-rank): replaces ATen batch_norm and SyncBatchNorm
+ *      (main.py:196,202,237,433; torch/nn/modules/_functions.py:10-205) ---- */
+int byol_bn_stats(const void* x, float* stats /* zeroed [2C] */, int M, int C, byol_stream_t stream);
+int byol_bn_finalize(const float* stats, double count, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float momentum, float eps, float* scale, float* shift, float* mean,
+                     float* invstd, int C, byol_stream_t stream);
+int byol_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                        float eps, float* scale, float* shift, int C, byol_stream_t stream);
+/* y = act(x*scale + shift + (resid | resid*rscale + rshift)) */
+int byol_bn_apply(const void* x, const float* scale, const float* shift, const void* resid, const float* rscale,
+                  const float* rshift, void* y, float* y_f32, int M, int C, int relu, byol_stream_t stream);
+/* s12 (zeroed [2C]) += [sum dz, sum dz*xhat]; mask_mode 0 none / 1 relu(x*scale+shift) / 2 act > 0 */
+int byol_bn_bwd_reduce(const void* g, const void* x, const void* act, const float* scale, const float* shift,
+                       const float* mean, const float* invstd, float* s12, int M, int C, int mask_mode,
+                       byol_stream_t stream);
+/* dy = gamma*invstd*(dz - s1/n - xhat*s2/n); dgamma/dbeta (optional) += rank-local sums */
+int byol_bn_bwd_apply(const void* g, const void* x, const void* act, const float* scale, const float* shift,
+                      const float* mean, const float* invstd, const float* gamma, const float* s12, double count,
+                      void* dy, void* dz_out, int M, int C, int mask_mode, const float* s12_local, float* dgamma,
+                      float* dbeta, byol_stream_t stream);
+int byol_col_sum(const void* x, float* out, int M, int C, int ld, int is_f32, byol_stream_t stream);
+
+/* ---- layout / pooling: torchvision ResNet stem and tail reached from main.py:237 ---- */
+int byol_nchw_to_nhwc8(const float* x, void* y, int N, int Cin, int H, int W, byol_stream_t stream);
+int byol_prep_weight(const float* w, void* w_fprop, void* w_dgrad, int Cout, int Cin, int Cpad, int KH, int KW,
+                     byol_stream_t stream);
+int byol_cast_f32_bf16(const float* x, void* y, int64_t n, byol_stream_t stream);
+int byol_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, int k, int s, int p,
+                     byol_stream_t stream);
+int byol_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, int k, int s, int p,
+                     byol_stream_t stream);
+int byol_avgpool_fwd(const void* x, float* y_f32, void* y_bf16, int N, int HW, int C, byol_stream_t stream);
+int byol_avgpool_bwd(const void* g_bf16, const float* g_f32, void* dx, int N, int HW, int C, byol_stream_t stream);
+
+/* ---- objective: replaces objective.py:6-25 (regression_loss / loss_function; Frobenius-normalised, rank-local) ----
+ * workspace: 6 doubles; loss: 1 float; saved: 6 floats consumed by byol_loss_bwd. */
+int byol_loss_fwd(const float* q1, const float* q2, const float* z1, const float* z2, int rows, int dim,
+                  double* workspace, float* loss, float* saved, byol_stream_t stream);
+int byol_loss_bwd(const float* q1, const float* q2, const float* z1, const float* z2, const float* saved,
+                  const float* grad_out, float* dq1, float* dq2, int rows, int dim, byol_stream_t stream);
+
+/* ---- target network: replaces CosEMA.forward, main.py:159-162.  mean = fl(fl(a*x) + fl(d*mean)), bit-exact ---- */
+int byol_ema_update(const float* x, float* mean, float one_minus_decay, float decay, int64_t n,
+                    byol_stream_t stream);
+
+/* ---- optimizer: replaces LARS.apply_adaptive_lrs + SGD(momentum).step, optimizers/lars.py:84-127 ----
+ * p_ptrs / g_ptrs / m_ptrs: device arrays of num_tensors fp32 pointers (m_ptrs may be NULL: no momentum);
+ * chunk tables split the tensors into <= 16384-element work items; norms: 2*num_tensors doubles (scratch). */
+int byol_lars_sgd_step(const void* p_ptrs, const void* g_ptrs, const void* m_ptrs, const int64_t* chunk_start,
+                       const int* chunk_len, const int* chunk_tensor, int num_chunks, const float* wd,
+                       const float* lr, const int* ignore, int num_tensors, double* norms, float trust_coef,
+                       float eps, float momentum, int first_step, byol_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BYOL_B200_H */
