@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .lars import LARS
+from .lars import LARS  # noqa: F401 (re-exported)
 from .objective import loss_function
 
 
