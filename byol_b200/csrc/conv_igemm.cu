@@ -46,6 +46,7 @@ struct ConvGemmParams {
   int tiles_n;
   int out_fp32;
   int relu;
+  int small_src;   // 1: the gathered tensor has < 2^31 elements (32-bit element offsets are safe)
 };
 
 template <int BN, int STAGES>
@@ -262,57 +263,120 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     const int chunk = tid & 7;   // 16-byte chunk inside the 128-byte k-row
     const int row0 = tid >> 3;   // rows row0 + 16*i
     int it = 0;                  // k-block iteration counter across tiles
+    // Fast path (stride-1 source mapping, C a multiple of 64, <= 32 taps, < 2^31 elements): one k-block is 64
+    // channels of ONE tap, so the tap counters advance without divisions, every row needs just
+    // "base offset + tap offset", and padding is a per-row bitmask over the taps computed once per tile.
+    // The stride-2 dgrad mapping (div == 2) fits too: a tap is valid only if it has the parity of (o + pad), and
+    // then src = ((o + pad) >> 1) - (k >> 1), i.e. again "row base + tap offset"; parity goes into the bitmask.
+    const bool fast = (p.C % BK == 0) && (p.KH * p.KW <= 32) && p.small_src;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.tiles_n) * BM;
-      int bh[8], bw[8];
-      int64_t ioff[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int m = m0 + row0 + 16 * i;
-        if (m < p.M) {
-          int ow = m % p.Wo;
-          int t = m / p.Wo;
-          int oh = t % p.Ho;
-          int n = t / p.Ho;
-          bh[i] = oh * p.mul + p.base;
-          bw[i] = ow * p.mul + p.base;
-          ioff[i] = (int64_t)n * p.Hs * p.Ws * p.C;
-        } else {
-          bh[i] = -(1 << 28);  // never valid
-          bw[i] = -(1 << 28);
-          ioff[i] = 0;
-        }
-      }
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        const int k0 = kb * BK + chunk * 8;
-        const bool kvalid = k0 < p.Kg;
-        const int tap = k0 / p.C;
-        const int cc = k0 - tap * p.C;
-        const int kh = tap / p.KW;
-        const int kw = tap - kh * p.KW;
-        const int dh = kh * p.dk, dw = kw * p.dk;
-        const uint32_t stage_base = smem_u32(smemA + s * A_STAGE_BYTES);
+      if (fast) {
+        uint32_t mask[8];
+        int roff[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          int sh = bh[i] + dh, sw = bw[i] + dw;
-          bool v = kvalid && sh >= 0 && sw >= 0;
-          if (p.div == 2) {
-            v = v && ((sh | sw) & 1) == 0;
-            sh >>= 1;
-            sw >>= 1;
+          const int m = m0 + row0 + 16 * i;
+          mask[i] = 0u;
+          roff[i] = 0;
+          if (m < p.M) {
+            const int ow = m % p.Wo;
+            const int t = m / p.Wo;
+            const int oh = t % p.Ho;
+            const int n = t / p.Ho;
+            const int bh = oh * p.mul + p.base, bw = ow * p.mul + p.base;
+            const int sft = p.div == 2 ? 1 : 0;
+            roff[i] = ((n * p.Hs + (bh >> sft)) * p.Ws + (bw >> sft)) * p.C;
+            int tapi = 0;
+            for (int kh = 0; kh < p.KH; ++kh)
+              for (int kw = 0; kw < p.KW; ++kw, ++tapi) {
+                int sh = bh + kh * p.dk, sw = bw + kw * p.dk;
+                bool ok = sh >= 0 && sw >= 0;
+                if (p.div == 2) { ok = ok && ((sh | sw) & 1) == 0; sh >>= 1; sw >>= 1; }
+                if (ok && sh < p.Hs && sw < p.Ws) mask[i] |= 1u << tapi;
+              }
           }
-          v = v && sh < p.Hs && sw < p.Ws;
-          const bf16* g = v ? p.src + ioff[i] + ((int64_t)sh * p.Ws + sw) * p.C + cc : p.src;
-          cp_async16_zfill(stage_base + sw128_offset(row0 + 16 * i, chunk), g, v);
         }
-        cp_async_commit();
-        if (it >= GATHER_LAG) {
-          cp_async_wait<GATHER_LAG>();
-          fence_proxy_async_smem();
-          mbar_arrive(&full_bar[(it - GATHER_LAG) % STAGES]);
+        int kh = 0, kw = 0, cc = 0, tapi = 0;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          if (it >= GATHER_LAG) {
+            cp_async_wait<GATHER_LAG - 1>();
+            fence_proxy_async_smem();
+            mbar_arrive(&full_bar[(it - GATHER_LAG) % STAGES]);
+          }
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const int tapoff = (p.div == 2 ? -((kh >> 1) * p.Ws + (kw >> 1)) : (kh * p.Ws + kw) * p.dk) * p.C + cc +
+                             chunk * 8;
+          const uint32_t stage_base = smem_u32(smemA + s * A_STAGE_BYTES);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool v = (mask[i] >> tapi) & 1u;
+            const bf16* g = v ? p.src + (roff[i] + tapoff) : p.src;
+            cp_async16_zfill(stage_base + sw128_offset(row0 + 16 * i, chunk), g, v);
+          }
+          cp_async_commit();
+          cc += BK;
+          if (cc >= p.C) {
+            cc = 0;
+            ++tapi;
+            if (++kw == p.KW) { kw = 0; ++kh; }
+          }
+        }
+      } else {
+        int bh[8], bw[8];
+        int64_t ioff[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int m = m0 + row0 + 16 * i;
+          if (m < p.M) {
+            int ow = m % p.Wo;
+            int t = m / p.Wo;
+            int oh = t % p.Ho;
+            int n = t / p.Ho;
+            bh[i] = oh * p.mul + p.base;
+            bw[i] = ow * p.mul + p.base;
+            ioff[i] = (int64_t)n * p.Hs * p.Ws * p.C;
+          } else {
+            bh[i] = -(1 << 28);  // never valid
+            bw[i] = -(1 << 28);
+            ioff[i] = 0;
+          }
+        }
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          // Publish the stage issued GATHER_LAG iterations ago BEFORE blocking on a free slot: otherwise the MMA
+          // warp would wait for this thread to come round the loop although the data landed long ago.
+          if (it >= GATHER_LAG) {
+            cp_async_wait<GATHER_LAG - 1>();
+            fence_proxy_async_smem();
+            mbar_arrive(&full_bar[(it - GATHER_LAG) % STAGES]);
+          }
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const int k0 = kb * BK + chunk * 8;
+          const bool kvalid = k0 < p.Kg;
+          const int tap = k0 / p.C;
+          const int cc = k0 - tap * p.C;
+          const int kh = tap / p.KW;
+          const int kw = tap - kh * p.KW;
+          const int dh = kh * p.dk, dw = kw * p.dk;
+          const uint32_t stage_base = smem_u32(smemA + s * A_STAGE_BYTES);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            int sh = bh[i] + dh, sw = bw[i] + dw;
+            bool v = kvalid && sh >= 0 && sw >= 0;
+            if (p.div == 2) {
+              v = v && ((sh | sw) & 1) == 0;
+              sh >>= 1;
+              sw >>= 1;
+            }
+            v = v && sh < p.Hs && sw < p.Ws;
+            const bf16* g = v ? p.src + ioff[i] + ((int64_t)sh * p.Ws + sw) * p.C + cc : p.src;
+            cp_async16_zfill(stage_base + sw128_offset(row0 + 16 * i, chunk), g, v);
+          }
+          cp_async_commit();
         }
       }
     }
@@ -393,15 +457,20 @@ struct WgradParams {
   int stride, pad;
   int M;             // Nimg*Ho*Wo
   int Cout, Cin_real;
-  int tiles_co, tiles_ci;
+  int tiles_co, tiles_n;
   int splits, kb_per_split, num_kb_total;
-  int fold_kw;       // 1: C == 8 and the KW taps are folded into the channel dimension (stem): B column = kw*8 + c
+  int Cg;            // channels per column group: C, or 64 in folded (stem) mode
+  int groups;        // number of column groups: KH*KW taps, or KH in folded mode
+  int fold_kw;       // 1: C == 8 and the KW taps are folded into the 64-wide column group: column = kw*8 + c
   int vec4;          // 1: 1x1 conv with 16-byte aligned gradient rows: accumulate with red.global.add.v4.f32
+  int small_src;     // 1: 32-bit element offsets are safe
 };
 
 static constexpr int WG_KROWS = 64;  // pixels per k-block
 static constexpr int WG_A_STAGE = 2 * WG_KROWS * 128;  // two 64-channel chunks (co tile = 128)
 
+// The GEMM N dimension is the concatenation of all taps: column = group*Cg + c (group = tap), tiled by BN, so a
+// CTA whose BN spans several taps re-uses its dY tile (A operand) for all of them.
 template <int BN, int STAGES, bool B_TMA>
 __global__ void __launch_bounds__(192, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
@@ -420,20 +489,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   int bid = blockIdx.x;
-  const int tile_ci = bid % p.tiles_ci;  bid /= p.tiles_ci;
+  const int tile_n = bid % p.tiles_n;    bid /= p.tiles_n;
   const int tile_co = bid % p.tiles_co;  bid /= p.tiles_co;
-  const int split = bid % p.splits;      bid /= p.splits;
-  const int tap = bid;
-  // folded (stem) mode: one CTA group per kh, the kw taps live in the B columns
-  const int kh = p.fold_kw ? tap : tap / p.KW;
-  const int kw = p.fold_kw ? 0 : tap - kh * p.KW;
-  const int kh_tap = kh;
+  const int split = bid;
   const int co0 = tile_co * 128;
-  const int ci0 = tile_ci * BN;
+  const int n0 = tile_n * BN;            // first column of this tile in the concatenated (group, channel) space
   const int kb_begin = split * p.kb_per_split;
   int kb_end = kb_begin + p.kb_per_split;
   if (kb_end > p.num_kb_total) kb_end = p.num_kb_total;
   const int nkb = kb_end - kb_begin;   // host guarantees nkb >= 1
+  const int taps = p.KH * p.KW;
 
   if (warp == 5 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -457,92 +522,103 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   if (warp < 4) {
     if (!B_TMA) {
       // gather: 64 pixel rows x (NCH*8) 16-byte chunks per stage, 128 threads.  Thread t owns chunk column
-      // (t % CHUNKS) of rows r0 + ROW_STEP*i; pixel coordinates are advanced incrementally (no per-element division).
+      // (t % CHUNKS) -> a fixed (tap, channel) -> and PER_THREAD CONSECUTIVE pixels, so that coordinates and the
+      // source offset advance by plain increments (one division pair per k-block, none per element).
       constexpr int CHUNKS = NCH * 8;
       constexpr int PER_THREAD = WG_KROWS * CHUNKS / 128;
-      constexpr int ROW_STEP = 128 / CHUNKS;
       const int chunk = threadIdx.x % CHUNKS;
-      const int r0 = threadIdx.x / CHUNKS;
+      const int rbase = (threadIdx.x / CHUNKS) * PER_THREAD;
       const int ch64 = chunk >> 3, c16 = chunk & 7;
-      const int ci = p.fold_kw ? 0 : ci0 + chunk * 8;
-      const int kw_eff = p.fold_kw ? chunk : kw;          // folded: the chunk index is the kw tap
-      const bool cvalid = p.fold_kw ? (chunk < p.KW) : (ci < p.C);
-      const int dh = kh - p.pad, dw = kw_eff - p.pad;
+      const int col = n0 + chunk * 8;
+      const int group = col / p.Cg;
+      const int cw = col - group * p.Cg;
+      int kh, kw, ci;
+      bool cvalid = group < p.groups;
+      if (p.fold_kw) { kh = group; kw = cw >> 3; ci = 0; cvalid = cvalid && kw < p.KW; }
+      else           { kh = group / p.KW; kw = group - kh * p.KW; ci = cw; }
+      const int dh = kh - p.pad, dw = kw - p.pad;
+      const int64_t sC = (int64_t)p.stride * p.C;
       for (int it = 0; it < nkb; ++it) {
         const int kb = kb_begin + it;
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
+        if (it >= GATHER_LAG) {   // publish the older stage before blocking on a free slot (see conv_igemm_kernel)
+          cp_async_wait<GATHER_LAG - 1>();
+          fence_proxy_async_smem();
+          mbar_arrive(&full_bar[(it - GATHER_LAG) % STAGES]);
+        }
         mbar_wait(&empty_bar[s], ph ^ 1);
         const uint32_t stage_base = smem_u32(smemB + s * B_STAGE) + ch64 * (WG_KROWS * 128);
-        int m = kb * WG_KROWS + r0;
+        int m = kb * WG_KROWS + rbase;
         int ow = m % p.Wo;
         int t = m / p.Wo;
         int oh = t % p.Ho;
         int n = t / p.Ho;
+        int sw = ow * p.stride + dw;
+        int sh = oh * p.stride + dh;
+        bool hvalid = cvalid && sh >= 0 && sh < p.Hs;
+        int64_t off = (((int64_t)n * p.Hs + sh) * p.Ws + sw) * p.C + ci;
 #pragma unroll
         for (int i = 0; i < PER_THREAD; ++i) {
-          const int r = r0 + ROW_STEP * i;
-          const int sh = oh * p.stride + dh;
-          const int sw = ow * p.stride + dw;
-          const bool v = cvalid && m < p.M && sh >= 0 && sw >= 0 && sh < p.Hs && sw < p.Ws;
-          const bf16* g = v ? p.src + (((int64_t)n * p.Hs + sh) * p.Ws + sw) * p.C + ci : p.src;
-          cp_async16_zfill(stage_base + sw128_offset(r, c16), g, v);
-          m += ROW_STEP;
-          ow += ROW_STEP;
-          while (ow >= p.Wo) {
-            ow -= p.Wo;
+          const bool v = hvalid && m < p.M && sw >= 0 && sw < p.Ws;
+          cp_async16_zfill(stage_base + sw128_offset(rbase + i, c16), v ? p.src + off : p.src, v);
+          ++m;
+          sw += p.stride;
+          off += sC;
+          if (++ow == p.Wo) {
+            ow = 0;
             if (++oh == p.Ho) { oh = 0; ++n; }
+            sw = dw;
+            sh = oh * p.stride + dh;
+            hvalid = cvalid && sh >= 0 && sh < p.Hs;
+            off = (((int64_t)n * p.Hs + sh) * p.Ws + sw) * p.C + ci;
           }
         }
         cp_async_commit();
-        if (it >= GATHER_LAG) {
-          cp_async_wait<GATHER_LAG>();
-          fence_proxy_async_smem();
-          mbar_arrive(&full_bar[(it - GATHER_LAG) % STAGES]);
-        }
       }
       cp_async_wait<0>();
       fence_proxy_async_smem();
       for (int it = (nkb > GATHER_LAG ? nkb - GATHER_LAG : 0); it < nkb; ++it) mbar_arrive(&full_bar[it % STAGES]);
     }
-    // ---------------- epilogue: TMEM -> atomicAdd into fp32 gradient ----------------------
+    // ---------------- epilogue: TMEM -> L2 reductions into the fp32 gradient ----------------
     mbar_wait(accum_bar, 0);
     tc_fence_after_sync();
     const int co = co0 + warp * 32 + lane;
     const bool covalid = co < p.Cout;
-    const int taps = p.KH * p.KW;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
       tmem_ld_wait();
-      if (covalid) {
-        if (p.fold_kw) {
-          // column = kw*8 + ci ; tap index here is kh
-          float* gp = p.dw + ((int64_t)co * p.Cin_real) * taps + kh_tap * p.KW;
+      const int colb = n0 + c0;                // 32 columns never straddle a group (Cg is a multiple of 64)
+      const int group = colb / p.Cg;
+      const int cw0 = colb - group * p.Cg;
+      if (!covalid || group >= p.groups) continue;
+      if (p.fold_kw) {
+        // column = kw*8 + ci ; the group index is kh
+        float* gp = p.dw + ((int64_t)co * p.Cin_real) * taps + group * p.KW;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = c0 + j, kwj = col >> 3, cj = col & 7;
-            if (kwj < p.KW && cj < p.Cin_real) atomicAdd(gp + (int64_t)cj * taps + kwj, __uint_as_float(r[j]));
-          }
-        } else if (p.vec4) {
-          // 1x1: the 32 columns are contiguous in memory -> 8 vector reductions instead of 32 scalar ones
-          float* gp = p.dw + (int64_t)co * p.Cin_real + ci0 + c0;
+        for (int j = 0; j < 32; ++j) {
+          const int cwj = cw0 + j, kwj = cwj >> 3, cj = cwj & 7;
+          if (kwj < p.KW && cj < p.Cin_real) atomicAdd(gp + (int64_t)cj * taps + kwj, __uint_as_float(r[j]));
+        }
+      } else if (p.vec4) {
+        // 1x1: the 32 columns are contiguous in memory -> 8 vector reductions instead of 32 scalar ones
+        float* gp = p.dw + (int64_t)co * p.Cin_real + cw0;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (ci0 + c0 + j < p.Cin_real)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gp + j), "f"(__uint_as_float(r[j])),
-                           "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
-                           "f"(__uint_as_float(r[j + 3]))
-                           : "memory");
-          }
-        } else {
-          float* gp = p.dw + ((int64_t)co * p.Cin_real) * taps + tap;
+        for (int j = 0; j < 32; j += 4) {
+          if (cw0 + j < p.Cin_real)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gp + j), "f"(__uint_as_float(r[j])),
+                         "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
+                         "f"(__uint_as_float(r[j + 3]))
+                         : "memory");
+        }
+      } else {
+        float* gp = p.dw + ((int64_t)co * p.Cin_real) * taps + group;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            int ci = ci0 + c0 + j;
-            if (ci < p.Cin_real) atomicAdd(gp + (int64_t)ci * taps, __uint_as_float(r[j]));
-          }
+        for (int j = 0; j < 32; ++j) {
+          const int ci = cw0 + j;
+          if (ci < p.Cin_real) atomicAdd(gp + (int64_t)ci * taps, __uint_as_float(r[j]));
         }
       }
     }
@@ -585,7 +661,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           const uint32_t b_base = smem_u32(smemB + s * B_STAGE);
 #pragma unroll
           for (int c = 0; c < NCH; ++c)
-            tma_load_2d(b_base + c * (WG_KROWS * 128), &tmapB, &full_bar[s], ci0 + 64 * c, kb * WG_KROWS);
+            tma_load_2d(b_base + c * (WG_KROWS * 128), &tmapB, &full_bar[s], n0 + 64 * c, kb * WG_KROWS);
         }
       }
     }
@@ -713,6 +789,7 @@ extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const
   p.num_kb = (p.Kg + BK - 1) / BK;
   p.out_fp32 = out_fp32;
   p.relu = relu;
+  p.small_src = ((int64_t)Nimg * Hs * Ws * C < (1ll << 31) - (1ll << 24)) ? 1 : 0;
   const int BN = (Ndim > 64) ? 128 : 64;
   p.tiles_n = (Ndim + BN - 1) / BN;
   const int tiles_m = (p.M + BM - 1) / BM;
@@ -776,18 +853,24 @@ extern "C" int byol_conv_wgrad(const void* src, const void* dy, float* dw, int N
   p.M = (int)M64;
   p.Cout = Cout;
   p.Cin_real = Cin_real;
-  const int BN = (C > 128) ? 256 : (C > 64 ? 128 : 64);
   p.fold_kw = (C == 8 && KW <= 8 && KW > 1) ? 1 : 0;
+  BYOL_CHECK_ARG(p.fold_kw || C % 64 == 0 || KH * KW == 1, "byol_conv_wgrad: C=%d must be 8 (stem) or a multiple of 64", C);
+  p.Cg = p.fold_kw ? 64 : C;
+  p.groups = p.fold_kw ? KH : KH * KW;
+  const int ncols = p.groups * p.Cg;                       // concatenated (tap, channel) columns
+  const int BN = ncols > 128 ? 256 : (ncols > 64 ? 128 : 64);
   p.tiles_co = (Cout + 127) / 128;
-  p.tiles_ci = (C + BN - 1) / BN;
+  p.tiles_n = (ncols + BN - 1) / BN;
   p.num_kb_total = (p.M + WG_KROWS - 1) / WG_KROWS;
-  const int taps = p.fold_kw ? KH : KH * KW;
-  const int base_ctas = p.tiles_co * p.tiles_ci * taps;
+  p.small_src = ((int64_t)Nimg * Hs * Ws * C < (1ll << 31) - (1ll << 24)) ? 1 : 0;
+  const int taps = KH * KW;
+  const int base_ctas = p.tiles_co * p.tiles_n;
   // The epilogue adds 128 x BN fp32 values per CTA to the gradient with L2 reductions, so the split count trades
-  // parallelism against reduction traffic: aim for one resident wave (2 CTAs/SM fit only for BN = 64).
+  // parallelism against reduction traffic: exactly one resident wave (2 CTAs/SM fit only for BN = 64), rounded
+  // DOWN so that no second, nearly empty wave appears.
   p.vec4 = (taps == 1 && !p.fold_kw && Cin_real % 4 == 0 && ((uintptr_t)dw % 16 == 0)) ? 1 : 0;
   const int target_ctas = sm_count() * (BN == 64 ? 2 : 1);
-  int splits = (target_ctas + base_ctas - 1) / base_ctas;
+  int splits = target_ctas / base_ctas;
   int max_splits = (p.num_kb_total + 7) / 8;                // at least 8 k-blocks (512 pixels) per CTA
   if (max_splits < 1) max_splits = 1;
   if (splits > max_splits) splits = max_splits;
@@ -797,6 +880,7 @@ extern "C" int byol_conv_wgrad(const void* src, const void* dy, float* dw, int N
   const int grid = base_ctas * p.splits;
   const bool b_tma = !force_gather && KH == 1 && KW == 1 && stride == 1 && pad == 0;
 
+  BYOL_CHECK_ARG(!b_tma || C % 8 == 0, "byol_conv_wgrad: bad C");
   CUtensorMap ta, tb;
   if (make_tmap_2d(&ta, dy, (uint64_t)p.M, (uint64_t)Cout, (uint64_t)Cout, (uint32_t)WG_KROWS) != 0) return -3;
   if (b_tma) {
