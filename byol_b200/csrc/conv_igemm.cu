@@ -54,11 +54,13 @@ struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BN * 128;
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
-  static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;
-  // 4 epilogue warps x [32 rows][64 B]; the TMA 64-byte swizzle pattern repeats every 512 B, so every
-  // warp tile must start on a 512-byte boundary (here: 1024-aligned base + multiples of 2048)
-  static constexpr int STAGE_OUT_OFF = BAR_OFF + 1024;
-  static constexpr int TOTAL = STAGE_OUT_OFF + 4 * 2048 + 1024;  // +1024 alignment slack
+  // output staging: 4 epilogue warps x 2 buffers x [32 rows][64 B].  The TMA 64-byte swizzle pattern repeats every
+  // 512 B, so every buffer must start on a 512-byte boundary (here: 1024-aligned base + multiples of 2048).
+  static constexpr int STAGE_OUT_OFF = B_OFF + STAGES * B_STAGE_BYTES;
+  static constexpr int BAR_OFF = STAGE_OUT_OFF + 4 * 2 * 2048;
+  static constexpr int NEEDED = BAR_OFF + 256;
+  static constexpr int TOTAL = NEEDED + 768;   // slack for the run-time 1024-byte alignment of the base
+  static_assert(TOTAL <= 115712, "two CTAs per SM need <= 113 KB of dynamic shared memory each");
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -78,8 +80,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   using L = SmemLayout<BN, STAGES>;
   constexpr int MMA_WARP = A_TMA ? 4 : 8;
   constexpr int TMA_WARP = MMA_WARP + 1;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  if (smem + L::NEEDED > smem_raw + L::TOTAL) __trap();   // the dynamic smem base was less aligned than assumed
   uint8_t* smemA = smem + L::A_OFF;
   uint8_t* smemB = smem + L::B_OFF;
   uint64_t* full_bar = (uint64_t*)(smem + L::BAR_OFF);
@@ -123,8 +126,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     // staging tile, the warp sums its 32 rows per column from the same tile (lane = column) for the fused
     // BatchNorm statistics; the sums stay in registers across all tiles of this CTA that share a column block.
     const bool do_stats = p.col_sum != nullptr;
-    const uint32_t stage_base = smem_u32(stage_out + warp * 2048);
-    const uint8_t* stage_ptr = stage_out + warp * 2048;
+    // two staging buffers per warp: chunk i+1 is converted and staged while the TMA engine still reads chunk i
+    const uint32_t stage_base0 = smem_u32(stage_out + warp * 4096);
+    int sbuf = 0;
     float csum[BN / 32], csq[BN / 32];
 #pragma unroll
     for (int i = 0; i < BN / 32; ++i) { csum[i] = 0.f; csq[i] = 0.f; }
@@ -208,6 +212,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         } else {
           // stage this warp's [32 rows][32 cols] bf16 block: row = lane, 16-byte chunk j at (j ^ ((row >> 1) & 3))
           // (= the TMA 64-byte swizzle), which also spreads the 32 row-writes over all banks
+          const uint32_t stage_base = stage_base0 + (uint32_t)sbuf * 2048u;
+          if (lane == 0) tma_store_wait_read1();   // the store that used THIS buffer two chunks ago has read it
+          __syncwarp();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 q;
@@ -227,23 +234,36 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             tma_store_commit();
           }
           if (do_stats) {
-            // lane = column: sum the stored (bf16-rounded) values of this warp's valid rows
+            // lane = column: sum the stored (bf16-rounded) values of this warp's valid rows.  Fully unrolled:
+            // the swizzle term ((row >> 1) & 3) is a compile-time constant per row, so each row costs
+            // one ld.shared.u16 + shift + FADD + FFMA.
+            const uint32_t jc = (uint32_t)lane >> 3, e2 = ((uint32_t)lane & 7u) * 2u;
+            uint32_t offq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) offq[q] = stage_base + ((jc ^ (uint32_t)q) << 4) + e2;
             float s1 = 0.f, s2 = 0.f;
-            const int jc = lane >> 3, e2 = (lane & 7) * 2;
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) {
-              if (rr < rows_valid) {
-                const bf16 hv = *reinterpret_cast<const bf16*>(stage_ptr + rr * 64 + ((jc ^ ((rr >> 1) & 3)) << 4) + e2);
-                const float x = __bfloat162float(hv);
+            if (rows_valid == 32) {
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) {
+                uint16_t hv;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(offq[(rr >> 1) & 3] + (uint32_t)rr * 64u));
+                const float x = __uint_as_float((uint32_t)hv << 16);
                 s1 += x;
-                s2 += x * x;
+                s2 = fmaf(x, x, s2);
+              }
+            } else {
+              for (int rr = 0; rr < rows_valid; ++rr) {
+                uint16_t hv;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(offq[(rr >> 1) & 3] + (uint32_t)rr * 64u));
+                const float x = __uint_as_float((uint32_t)hv << 16);
+                s1 += x;
+                s2 = fmaf(x, x, s2);
               }
             }
             csum[ci] += s1;
             csq[ci] += s2;
           }
-          if (lane == 0) tma_store_wait_read();   // the staging tile may be overwritten after this
-          __syncwarp();
+          sbuf ^= 1;
         }
       }
     }
