@@ -47,7 +47,41 @@ struct ConvGemmParams {
   int out_fp32;
   int relu;
   int small_src;   // 1: the gathered tensor has < 2^31 elements (32-bit element offsets are safe)
+  // stride-2 dgrad by output parity ("parity mode"): the M dimension enumerates the pixels of dX class by class
+  // (class = (ih & 1, iw & 1)); a tile belongs to ONE class, for which only the taps with the parity of
+  // (coordinate + pad) contribute, so every role skips the other taps entirely.
+  int parity;      // 1: enabled
+  int Hh, Wh;      // dX spatial size / 2
+  int Mc;          // pixels per class = Nimg*Hh*Wh (a multiple of BM)
+  int ncls;        // number of classes with at least one tap
+  int cls_list[4]; // their ids (ph*2 + pw)
 };
+
+// per-tile geometry shared by all warp roles
+struct TileInfo {
+  int m0, n0, nkb;
+  int cls_idx, ph, pw, kh0, kw0, nkw;   // parity mode only
+};
+
+__device__ __forceinline__ TileInfo tile_info(const ConvGemmParams& p, int tile, int BN_) {
+  TileInfo t;
+  t.m0 = (tile / p.tiles_n) * BM;
+  t.n0 = (tile % p.tiles_n) * BN_;
+  t.nkb = p.num_kb;
+  t.cls_idx = 0; t.ph = 0; t.pw = 0; t.kh0 = 0; t.kw0 = 0; t.nkw = p.KW;
+  if (p.parity) {
+    t.cls_idx = t.m0 / p.Mc;
+    const int cls = p.cls_list[t.cls_idx];
+    t.ph = cls >> 1;
+    t.pw = cls & 1;
+    t.kh0 = (t.ph + p.base) & 1;            // p.base == pad in dgrad mode
+    t.kw0 = (t.pw + p.base) & 1;
+    const int nkh = (p.KH - t.kh0 + 1) >> 1;
+    t.nkw = (p.KW - t.kw0 + 1) >> 1;
+    t.nkb = nkh * t.nkw * (p.C / BK);
+  }
+  return t;
+}
 
 template <int BN, int STAGES>
 struct SmemLayout {
@@ -135,9 +169,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     int local = 0;
     int stat_n0 = -1;   // column offset the register accumulators currently belong to
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-      const int tile_n = tile % p.tiles_n;
-      const int m0 = (tile / p.tiles_n) * BM;
-      const int n0 = tile_n * BN;
+      const TileInfo ti = tile_info(p, tile, BN);
+      const int m0 = ti.m0;
+      const int n0 = ti.n0;
       if (do_stats && stat_n0 != n0) {
         if (stat_n0 >= 0) {
 #pragma unroll
@@ -155,8 +189,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       mbar_wait(&tfull_bar[acc], (uint32_t)((local >> 1) & 1));
       tc_fence_after_sync();
       const int mrow0 = m0 + warp * 32;
-      const int m = mrow0 + lane;
+      int m = mrow0 + lane;
       const bool mvalid = m < p.M;
+      if (p.parity) {
+        // row of the class-major enumeration -> row of dX: pixel (n, 2a + ph, 2b + pw)
+        const int mc = m - ti.cls_idx * p.Mc;
+        const int b = mc % p.Wh;
+        const int t2 = mc / p.Wh;
+        const int a = t2 % p.Hh;
+        const int n = t2 / p.Hh;
+        m = (n * p.Ho + 2 * a + ti.ph) * p.Wo + 2 * b + ti.pw;
+      }
       int rows_valid = p.M - mrow0;
       rows_valid = rows_valid < 0 ? 0 : (rows_valid > 32 ? 32 : rows_valid);
 #pragma unroll
@@ -201,7 +244,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        if (p.out_fp32) {
+        if (p.parity) {
+          // rows of one tile are not contiguous in dX: plain 16-byte stores (six layers per backward pass only)
+          if (mvalid) {
+            bf16* op = reinterpret_cast<bf16*>(p.dst) + (int64_t)m * p.ldc + nbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (nbase + j < p.Ndim) {
+                uint4 q;
+                q.x = pack_bf16x2(v[j], v[j + 1]);
+                q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                q.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(op + j) = q;
+              }
+            }
+          }
+        } else if (p.out_fp32) {
           if (mvalid) {
             float* op = reinterpret_cast<float*>(p.dst) + (int64_t)m * p.ldc + nbase;
 #pragma unroll
@@ -290,8 +349,55 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     // then src = ((o + pad) >> 1) - (k >> 1), i.e. again "row base + tap offset"; parity goes into the bitmask.
     const bool fast = (p.C % BK == 0) && (p.KH * p.KW <= 32) && p.small_src;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.tiles_n) * BM;
-      if (fast) {
+      const TileInfo ti = tile_info(p, tile, BN);
+      const int m0 = ti.m0;
+      if (p.parity) {
+        uint32_t mask[8];
+        int roff[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int mc = m0 + row0 + 16 * i - ti.cls_idx * p.Mc;
+          const int b = mc % p.Wh;
+          const int t2 = mc / p.Wh;
+          const int a = t2 % p.Hh;
+          const int n = t2 / p.Hh;
+          roff[i] = ((n * p.Hs + a) * p.Ws + b) * p.C;
+          mask[i] = 0u;
+          int tapi = 0;
+          for (int kh = ti.kh0; kh < p.KH; kh += 2)
+            for (int kw = ti.kw0; kw < p.KW; kw += 2, ++tapi) {
+              const int sh = a + ((ti.ph + p.base - kh) >> 1), sw = b + ((ti.pw + p.base - kw) >> 1);
+              if (sh >= 0 && sh < p.Hs && sw >= 0 && sw < p.Ws) mask[i] |= 1u << tapi;
+            }
+        }
+        int kh = ti.kh0, kw = ti.kw0, cc = 0, tapi = 0;
+        for (int kb = 0; kb < ti.nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          if (it >= GATHER_LAG) {
+            cp_async_wait<GATHER_LAG - 1>();
+            fence_proxy_async_smem();
+            mbar_arrive(&full_bar[(it - GATHER_LAG) % STAGES]);
+          }
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const int tapoff = (((ti.ph + p.base - kh) >> 1) * p.Ws + ((ti.pw + p.base - kw) >> 1)) * p.C + cc + chunk * 8;
+          const uint32_t stage_base = smem_u32(smemA + s * A_STAGE_BYTES);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool v = (mask[i] >> tapi) & 1u;
+            const bf16* g = v ? p.src + (roff[i] + tapoff) : p.src;
+            cp_async16_zfill(stage_base + sw128_offset(row0 + 16 * i, chunk), g, v);
+          }
+          cp_async_commit();
+          cc += BK;
+          if (cc >= p.C) {
+            cc = 0;
+            ++tapi;
+            kw += 2;
+            if (kw >= p.KW) { kw = ti.kw0; kh += 2; }
+          }
+        }
+      } else if (fast) {
         uint32_t mask[8];
         int roff[8];
 #pragma unroll
@@ -410,10 +516,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       int it = 0, local = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
         const int acc = local & 1;
+        const int nkb_tile = tile_info(p, tile, BN).nkb;
         mbar_wait(&tempty_bar[acc], (uint32_t)(((local >> 1) & 1) ^ 1));
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = 0; kb < nkb_tile; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
@@ -438,14 +545,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       constexpr uint32_t tx = (uint32_t)L::B_STAGE_BYTES + (A_TMA ? (uint32_t)A_STAGE_BYTES : 0u);
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n0 = (tile % p.tiles_n) * BN;
-        const int m0 = (tile / p.tiles_n) * BM;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const TileInfo ti = tile_info(p, tile, BN);
+        const int n0 = ti.n0;
+        const int m0 = ti.m0;
+        int kh = ti.kh0, kw = ti.kw0, cc = 0;
+        for (int kb = 0; kb < ti.nkb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_arrive_expect_tx(&full_bar[s], tx);
-          tma_load_2d(smem_u32(smemB + s * L::B_STAGE_BYTES), &tmapB, &full_bar[s], kb * BK, n0);
+          int kcol = kb * BK;
+          if (p.parity) {   // weight columns of the current class tap
+            kcol = (kh * p.KW + kw) * p.C + cc;
+            cc += BK;
+            if (cc >= p.C) { cc = 0; kw += 2; if (kw >= p.KW) { kw = ti.kw0; kh += 2; } }
+          }
+          tma_load_2d(smem_u32(smemB + s * L::B_STAGE_BYTES), &tmapB, &full_bar[s], kcol, n0);
           if (A_TMA) tma_load_2d(smem_u32(smemA + s * A_STAGE_BYTES), &tmapA, &full_bar[s], kb * BK, m0);
         }
       }
@@ -812,8 +927,26 @@ extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const
   p.small_src = ((int64_t)Nimg * Hs * Ws * C < (1ll << 31) - (1ll << 24)) ? 1 : 0;
   const int BN = (Ndim > 64) ? 128 : 64;
   p.tiles_n = (Ndim + BN - 1) / BN;
-  const int tiles_m = (p.M + BM - 1) / BM;
-  const bool a_tma = !force_gather && KH == 1 && KW == 1 && stride == 1 && pad == 0;
+  int tiles_m = (p.M + BM - 1) / BM;
+  if (mode == 1 && stride == 2 && Ho % 2 == 0 && Wo % 2 == 0 && C % BK == 0 && p.small_src && KH <= 3 && KW <= 3 &&
+      ((int64_t)Nimg * (Ho / 2) * (Wo / 2)) % BM == 0 && !out_fp32) {
+    p.parity = 1;
+    p.Hh = Ho / 2;
+    p.Wh = Wo / 2;
+    p.Mc = Nimg * p.Hh * p.Wh;
+    p.ncls = 0;
+    for (int cls = 0; cls < 4; ++cls) {
+      const int ph = cls >> 1, pw = cls & 1;
+      const int nkh = (KH - ((ph + pad) & 1) + 1) >> 1, nkw = (KW - ((pw + pad) & 1) + 1) >> 1;
+      if (nkh > 0 && nkw > 0) p.cls_list[p.ncls++] = cls;
+    }
+    if (p.ncls < 4) {   // pixels of classes without any tap receive zero gradient
+      cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)p.M * ldc * sizeof(bf16), stream);
+      if (e != cudaSuccess) { set_last_error("byol_conv_igemm: memset failed: %s", cudaGetErrorString(e)); return -2; }
+    }
+    tiles_m = p.ncls * (p.Mc / BM);
+  }
+  const bool a_tma = !force_gather && KH == 1 && KW == 1 && stride == 1 && pad == 0;   // never true in parity mode
 
   CUtensorMap ta, tb, tc;
   memset(&ta, 0, sizeof(ta));

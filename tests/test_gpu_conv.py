@@ -23,6 +23,9 @@ CONV_CASES = [
     ("3x3s2_128_128", 1, 28, 28, 128, 128, 128, 3, 2, 1),
     ("1x1s2_256_512", 1, 28, 28, 256, 256, 512, 1, 2, 0),
     ("3x3_512_512_7", 3, 7, 7, 512, 512, 512, 3, 1, 1),
+    ("3x3s2_parity", 2, 16, 16, 128, 128, 128, 3, 2, 1),     # dgrad runs in output-parity mode (Mc % 128 == 0)
+    ("1x1s2_parity", 2, 16, 16, 256, 256, 512, 1, 2, 0),
+    ("3x3s2_parity_64", 4, 16, 16, 64, 64, 128, 3, 2, 1),
     ("stem7x7", 2, 32, 32, 3, 8, 64, 7, 2, 3),
 ]
 
@@ -108,6 +111,22 @@ def test_conv_wgrad(cuda, case, force_gather):
     ops.conv_wgrad(xd, dy.to(cuda, torch.bfloat16), dw, k, k, s, p, force_gather=force_gather)
     torch.cuda.synchronize()
     assert_close("wgrad_acc[%s]" % name, dw, 2 * ref, atol=4e-3 * float(ref.abs().max()), rtol=0)
+
+
+def test_conv_dgrad_parity_with_residual(cuda):
+    """BasicBlock-style strided 3x3 dgrad with the residual gradient added in the epilogue (parity mode)."""
+    from byol_b200 import ops
+    case = ("3x3s2_parity", 2, 16, 16, 128, 128, 128, 3, 2, 1)
+    name, n, h, w, cin, cpad, cout, k, s, p = case
+    _, wt, _ = _mk(case, cuda)
+    g = torch.Generator().manual_seed(19)
+    dy = R.bf16_round(torch.randn(n, 8, 8, cout, generator=g))
+    resid = R.bf16_round(torch.randn(n, h, w, cin, generator=g))
+    _, w_d = ops.prep_weight(wt.to(cuda), cpad=cpad, want_dgrad=True)
+    ref = R.conv_dgrad_ref(dy, wt, (h, w), s, p) + resid
+    dx = ops.conv_dgrad(dy.to(cuda, torch.bfloat16), w_d, h, w, k, k, s, p, resid=resid.to(cuda, torch.bfloat16))
+    torch.cuda.synchronize()
+    assert_close("dgrad_parity_resid", dx, ref, atol=1e-2 * float(ref.abs().max()), rtol=0)
 
 
 LINEAR_CASES = [("head1", 64, 2048, 4096), ("head2", 64, 4096, 256), ("cls", 96, 2048, 1000), ("pred1", 200, 256, 4096)]
