@@ -27,6 +27,8 @@ _SIGNATURES = {
     "byol_bn_stats": [c_void_p, c_void_p, c_int, c_int, c_void_p],
     "byol_bn_finalize": [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p,
                          c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "byol_bn_finalize_lanes": [c_void_p, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_int, c_void_p],
     "byol_bn_eval_coeffs": [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p],
     "byol_bn_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                       c_int, c_void_p],
@@ -37,6 +39,7 @@ _SIGNATURES = {
     "byol_col_sum": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "byol_nchw_to_nhwc8": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "byol_prep_weight": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "byol_prep_weight_fold": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "byol_cast_f32_bf16": [c_void_p, c_void_p, c_int64, c_void_p],
     "byol_maxpool_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "byol_maxpool_bwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],

@@ -88,6 +88,39 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, double count
   }
 }
 
+// Same for up to 4 "lanes" (forward passes that ran this layer in lock-step, each with its own gamma/beta set and
+// its own batch statistics) in ONE launch; the running statistics are updated lane after lane, i.e. in the order
+// the reference's four sequential forward passes would update them (main.py:244-247).
+struct LanePtrs { const float* p[4]; };
+__global__ void bn_finalize_lanes_kernel(const float* __restrict__ stats, double count, LanePtrs gamma, LanePtrs beta,
+                                         float* __restrict__ running_mean, float* __restrict__ running_var,
+                                         float momentum, float eps, float* __restrict__ coeffs, int C, int L) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float rm = running_mean != nullptr ? running_mean[c] : 0.f;
+  float rv = running_var != nullptr ? running_var[c] : 0.f;
+  for (int l = 0; l < L; ++l) {
+    const float* st = stats + (int64_t)l * 2 * C;
+    double mean = (double)st[c] / count;
+    double var = (double)st[C + c] / count - mean * mean;   // biased
+    if (var < 0.0) var = 0.0;
+    float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    float sc = gamma.p[l][c] * invstd;
+    float* co = coeffs + (int64_t)l * 4 * C;
+    co[c] = sc;
+    co[C + c] = beta.p[l][c] - (float)mean * sc;
+    co[2 * C + c] = (float)mean;
+    co[3 * C + c] = invstd;
+    double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    rm = (1.f - momentum) * rm + momentum * (float)mean;
+    rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+  }
+  if (running_mean != nullptr) {
+    running_mean[c] = rm;
+    running_var[c] = rv;
+  }
+}
+
 // eval mode: scale/shift from running statistics
 __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                       const float* __restrict__ running_mean, const float* __restrict__ running_var,
@@ -416,6 +449,22 @@ extern "C" int byol_bn_finalize(const float* stats, double count, const float* g
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(stats, count, gamma, beta, running_mean, running_var,
                                                          momentum, eps, scale, shift, mean, invstd, C);
   return check_launch("bn_finalize_kernel");
+}
+
+// stats: [L][2C]; coeffs: [L][4][C]; gamma_l / beta_l for l < L (L <= 4)
+extern "C" int byol_bn_finalize_lanes(const float* stats, double count, int L, const float* gamma0, const float* beta0,
+                                      const float* gamma1, const float* beta1, const float* gamma2,
+                                      const float* beta2, const float* gamma3, const float* beta3,
+                                      float* running_mean, float* running_var, float momentum, float eps,
+                                      float* coeffs, int C, cudaStream_t stream) {
+  BYOL_CHECK_ARG(stats && coeffs && L >= 1 && L <= 4 && C > 0 && count > 0, "byol_bn_finalize_lanes: bad args");
+  LanePtrs g, b;
+  g.p[0] = gamma0; g.p[1] = gamma1; g.p[2] = gamma2; g.p[3] = gamma3;
+  b.p[0] = beta0; b.p[1] = beta1; b.p[2] = beta2; b.p[3] = beta3;
+  for (int l = 0; l < L; ++l) BYOL_CHECK_ARG(g.p[l] && b.p[l], "byol_bn_finalize_lanes: null gamma/beta for lane %d", l);
+  bn_finalize_lanes_kernel<<<(C + 127) / 128, 128, 0, stream>>>(stats, count, g, b, running_mean, running_var, momentum,
+                                                               eps, coeffs, C, L);
+  return check_launch("bn_finalize_lanes_kernel");
 }
 
 extern "C" int byol_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,

@@ -50,6 +50,7 @@ struct ConvGemmParams {
   // stride-2 dgrad by output parity ("parity mode"): the M dimension enumerates the pixels of dX class by class
   // (class = (ih & 1, iw & 1)); a tile belongs to ONE class, for which only the taps with the parity of
   // (coordinate + pad) contribute, so every role skips the other taps entirely.
+  int fold;        // 1: stem layout: C == 8, one k-block per kh, K column = kw*8 + c (kw padded to 8)
   int parity;      // 1: enabled
   int Hh, Wh;      // dX spatial size / 2
   int Mc;          // pixels per class = Nimg*Hh*Wh (a multiple of BM)
@@ -351,7 +352,48 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileInfo ti = tile_info(p, tile, BN);
       const int m0 = ti.m0;
-      if (p.parity) {
+      if (p.fold) {
+        // stem: k-block = kh, this thread's 16-byte chunk = kw: the 8 chunks of a row are 128 contiguous bytes
+        uint32_t mask[8];   // bit kh: (kh, this thread's kw) lies inside the image
+        int roff[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = m0 + row0 + 16 * i;
+          mask[i] = 0u;
+          roff[i] = 0;
+          if (m < p.M) {
+            const int ow = m % p.Wo;
+            const int t = m / p.Wo;
+            const int oh = t % p.Ho;
+            const int n = t / p.Ho;
+            const int bh = oh * p.mul + p.base, bw = ow * p.mul + p.base;
+            const int sw = bw + chunk;
+            roff[i] = ((n * p.Hs + bh) * p.Ws + sw) * 8;
+            if (chunk < p.KW && sw >= 0 && sw < p.Ws)
+              for (int kh = 0; kh < p.KH; ++kh)
+                if (bh + kh >= 0 && bh + kh < p.Hs) mask[i] |= 1u << kh;
+          }
+        }
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          if (it >= GATHER_LAG) {
+            cp_async_wait<GATHER_LAG - 1>();
+            fence_proxy_async_smem();
+            mbar_arrive(&full_bar[(it - GATHER_LAG) % STAGES]);
+          }
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const int tapoff = kb * p.Ws * 8;
+          const uint32_t stage_base = smem_u32(smemA + s * A_STAGE_BYTES);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool v = (mask[i] >> kb) & 1u;
+            const bf16* g = v ? p.src + (roff[i] + tapoff) : p.src;
+            cp_async16_zfill(stage_base + sw128_offset(row0 + 16 * i, chunk), g, v);
+          }
+          cp_async_commit();
+        }
+      } else if (p.parity) {
         uint32_t mask[8];
         int roff[8];
 #pragma unroll
@@ -919,6 +961,10 @@ extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const
   p.M = (int)M64;
   p.Ndim = Ndim;
   p.Kg = KH * KW * C;
+  // stem layout (weights made by byol_prep_weight with fold = 1): K = KH * 64, column = kh*64 + kw*8 + c
+  p.fold = (mode == 0 && C == 8 && KW > 1 && KW <= 8 && KH <= 32 && ldw == KH * 64 &&
+            (int64_t)Nimg * Hs * Ws * C < (1ll << 31) - (1ll << 24)) ? 1 : 0;
+  if (p.fold) p.Kg = KH * 64;
   BYOL_CHECK_ARG(ldw >= p.Kg && ldw % 8 == 0, "byol_conv_igemm: bad ldw=%d (Kg=%d)", ldw, p.Kg);
   p.ldc = ldc;
   p.num_kb = (p.Kg + BK - 1) / BK;

@@ -51,6 +51,22 @@ __global__ void prep_weight_kernel(const float* __restrict__ w, bf16* __restrict
   }
 }
 
+// stem (folded) fprop layout: w fp32 [Cout][Cin<=8][KH][KW<=8] -> wf bf16 [Cout][KH][8 kw slots][8 channels]
+__global__ void prep_weight_fold_kernel(const float* __restrict__ w, bf16* __restrict__ wf, int Cout, int Cin, int KH,
+                                        int KW) {
+  const int64_t total = (int64_t)Cout * KH * 64;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 7);
+    const int kw = (int)((i >> 3) & 7);
+    const int64_t t = i >> 6;
+    const int kh = (int)(t % KH);
+    const int co = (int)(t / KH);
+    float v = 0.f;
+    if (c < Cin && kw < KW) v = __ldg(w + (((int64_t)co * Cin + c) * KH + kh) * KW + kw);
+    wf[i] = __float2bfloat16_rn(v);
+  }
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16_rn(x[i]);
@@ -248,6 +264,15 @@ extern "C" int byol_prep_weight(const float* w, void* w_fprop, void* w_dgrad, in
   prep_weight_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, (bf16*)w_fprop, (bf16*)w_dgrad, Cout, Cin, Cpad,
                                                               KH * KW);
   return check_launch("prep_weight_kernel");
+}
+
+// stem layout for byol_conv_igemm's folded mode (C = 8 input channels, KW <= 8): w_fprop is [Cout][KH*64]
+extern "C" int byol_prep_weight_fold(const float* w, void* w_fprop, int Cout, int Cin, int KH, int KW,
+                                     cudaStream_t stream) {
+  BYOL_CHECK_ARG(w && w_fprop && Cout > 0 && Cin > 0 && Cin <= 8 && KW <= 8 && KH > 0, "byol_prep_weight_fold: bad args");
+  const int64_t total = (int64_t)Cout * KH * 64;
+  prep_weight_fold_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, (bf16*)w_fprop, Cout, Cin, KH, KW);
+  return check_launch("prep_weight_fold_kernel");
 }
 
 extern "C" int byol_cast_f32_bf16(const float* x, void* y, int64_t n, cudaStream_t stream) {

@@ -29,7 +29,7 @@ F32 = torch.float32
 class _Unit(object):
     """One conv/linear (+ optional BN) layer: static geometry plus offsets into the flat parameter vector."""
     __slots__ = ("idx", "kind", "cin", "cout", "cpad", "k", "stride", "pad", "w_off", "w_numel", "b_off", "bn",
-                 "g_off", "beta_off", "name", "want_dgrad")
+                 "g_off", "beta_off", "name", "want_dgrad", "fold", "kcols")
 
 
 class _Block(object):
@@ -40,13 +40,13 @@ class _Weights(object):
     """bf16 tensor-core layouts of one weight set (online or target)."""
 
     def __init__(self, units, device, want_dgrad):
-        nf = sum(u.cout * u.k * u.k * u.cpad for u in units)
+        nf = sum(u.cout * u.kcols for u in units)
         self.pool_f = torch.empty(nf, dtype=BF16, device=device)
         self.wf, self.wd = [], []
         off = 0
         for u in units:
-            n = u.cout * u.k * u.k * u.cpad
-            self.wf.append(self.pool_f[off:off + n].view(u.cout, u.k * u.k * u.cpad))
+            n = u.cout * u.kcols
+            self.wf.append(self.pool_f[off:off + n].view(u.cout, u.kcols))
             off += n
         if want_dgrad:
             nd = sum(u.cin * u.k * u.k * u.cout for u in units if u.want_dgrad)
@@ -141,6 +141,9 @@ class Engine(object):
             u.kind, u.cin, u.cout, u.k, u.stride, u.pad = "linear", mod.in_features, mod.out_features, 1, 1, 0
             u.b_off = self.offsets[id(mod.bias)] if mod.bias is not None else -1
         u.cpad = (u.cin + 7) // 8 * 8
+        # stem (3 input channels, 7x7): folded weight layout [Cout][KH*64] (see byol_prep_weight_fold)
+        u.fold = u.kind == "conv" and u.cpad == 8 and 1 < u.k <= 8
+        u.kcols = u.k * 64 if u.fold else u.k * u.k * u.cpad
         u.w_off = self.offsets[id(mod.weight)]
         u.w_numel = mod.weight.numel()
         u.bn = bn
@@ -194,8 +197,11 @@ class Engine(object):
     def prep_weights(self, flat, wset, want_dgrad):
         for u in self.units:
             w = flat[u.w_off:u.w_off + u.w_numel].view(u.cout, u.cin, u.k, u.k)
-            ops.prep_weight(w, cpad=u.cpad, want_dgrad=want_dgrad and u.want_dgrad, out_f=wset.wf[u.idx],
-                            out_d=wset.wd[u.idx])
+            if u.fold:
+                ops.prep_weight_fold(w, out_f=wset.wf[u.idx])
+            else:
+                ops.prep_weight(w, cpad=u.cpad, want_dgrad=want_dgrad and u.want_dgrad, out_f=wset.wf[u.idx],
+                                out_d=wset.wd[u.idx])
 
     # ------------------------------------------------------------------------------------------
     # forward building blocks (lists are per lane)
@@ -222,10 +228,9 @@ class Engine(object):
             if self.sync and self.world() > 1:
                 comm.allreduce_sum_(stats)
                 count = rows * self.world()
-            for i, (flat, _, _) in enumerate(lanes):
-                ops.bn_finalize(stats[i * 2 * C:(i + 1) * 2 * C], count, flat[u.g_off:u.g_off + C],
-                                flat[u.beta_off:u.beta_off + C], bn.running_mean, bn.running_var, bn.momentum, bn.eps,
-                                coeffs[i])
+            ops.bn_finalize_lanes(stats, count, [flat[u.g_off:u.g_off + C] for flat, _, _ in lanes],
+                                  [flat[u.beta_off:u.beta_off + C] for flat, _, _ in lanes], bn.running_mean,
+                                  bn.running_var, bn.momentum, bn.eps, coeffs)
         else:
             for i, (flat, _, _) in enumerate(lanes):
                 ops.bn_eval_coeffs(flat[u.g_off:u.g_off + C], flat[u.beta_off:u.beta_off + C], bn.running_mean,

@@ -71,6 +71,16 @@ def prep_weight(w, cpad=None, want_dgrad=True, out_f=None, out_d=None):
     return out_f, (out_d if want_dgrad else None)
 
 
+def prep_weight_fold(w, out_f=None):
+    """Stem layout: fp32 [Cout, Cin<=8, KH, KW<=8] -> bf16 [Cout, KH*64] (column = kh*64 + kw*8 + c)."""
+    _chk(w, F32, "w")
+    cout, cin, kh, kw = w.shape
+    if out_f is None:
+        out_f = torch.empty((cout, kh * 64), dtype=BF16, device=w.device)
+    check(lib.byol_prep_weight_fold(_ptr(w), _ptr(out_f), cout, cin, kh, kw, _stream()), "byol_prep_weight_fold")
+    return out_f
+
+
 def cast_bf16(x, out=None):
     _chk(x, F32, "x")
     if out is None:
@@ -162,6 +172,18 @@ def bn_finalize(stats, count, gamma, beta, running_mean, running_var, momentum, 
     check(lib.byol_bn_finalize(_ptr(stats), float(count), _ptr(gamma), _ptr(beta), _ptr(running_mean),
                                _ptr(running_var), float(momentum), float(eps), _ptr(coeffs[0]), _ptr(coeffs[1]),
                                _ptr(coeffs[2]), _ptr(coeffs[3]), c, _stream()), "byol_bn_finalize")
+    return coeffs
+
+
+def bn_finalize_lanes(stats, count, gammas, betas, running_mean, running_var, momentum, eps, coeffs):
+    """One launch for all lock-step lanes: stats [L*2C], coeffs [L,4,C]; gammas/betas: per-lane fp32 [C] tensors."""
+    L = len(gammas)
+    c = gammas[0].numel()
+    g = [_ptr(t) for t in gammas] + [0] * (4 - L)
+    b = [_ptr(t) for t in betas] + [0] * (4 - L)
+    check(lib.byol_bn_finalize_lanes(_ptr(stats), float(count), L, g[0], b[0], g[1], b[1], g[2], b[2], g[3], b[3],
+                                     _ptr(running_mean), _ptr(running_var), float(momentum), float(eps),
+                                     _ptr(coeffs), c, _stream()), "byol_bn_finalize_lanes")
     return coeffs
 
 

@@ -54,6 +54,12 @@ int byol_bn_stats(const void* x, float* stats /* zeroed [2C] */, int M, int C, b
 int byol_bn_finalize(const float* stats, double count, const float* gamma, const float* beta, float* running_mean,
                      float* running_var, float momentum, float eps, float* scale, float* shift, float* mean,
                      float* invstd, int C, byol_stream_t stream);
+/* same for L <= 4 lock-step lanes in one launch: stats [L][2C], coeffs [L][4][C] = scale, shift, mean, invstd;
+ * running statistics are updated lane after lane (the order of the reference's four forward passes) */
+int byol_bn_finalize_lanes(const float* stats, double count, int L, const float* gamma0, const float* beta0,
+                           const float* gamma1, const float* beta1, const float* gamma2, const float* beta2,
+                           const float* gamma3, const float* beta3, float* running_mean, float* running_var,
+                           float momentum, float eps, float* coeffs, int C, byol_stream_t stream);
 int byol_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                         float eps, float* scale, float* shift, int C, byol_stream_t stream);
 /* y = act(x*scale + shift + (resid | resid*rscale + rshift)) */
@@ -74,6 +80,8 @@ int byol_col_sum(const void* x, float* out, int M, int C, int ld, int is_f32, by
 int byol_nchw_to_nhwc8(const float* x, void* y, int N, int Cin, int H, int W, byol_stream_t stream);
 int byol_prep_weight(const float* w, void* w_fprop, void* w_dgrad, int Cout, int Cin, int Cpad, int KH, int KW,
                      byol_stream_t stream);
+/* stem layout ([Cout][KH*64], column = kh*64 + kw*8 + c) selected by byol_conv_igemm when C == 8 and ldw == KH*64 */
+int byol_prep_weight_fold(const float* w, void* w_fprop, int Cout, int Cin, int KH, int KW, byol_stream_t stream);
 int byol_cast_f32_bf16(const float* x, void* y, int64_t n, byol_stream_t stream);
 int byol_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, int k, int s, int p,
                      byol_stream_t stream);

@@ -113,6 +113,27 @@ def test_conv_wgrad(cuda, case, force_gather):
     assert_close("wgrad_acc[%s]" % name, dw, 2 * ref, atol=4e-3 * float(ref.abs().max()), rtol=0)
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 32), (3, 30, 26), (1, 224, 224)])
+def test_stem_folded_layout(cuda, shape):
+    """7x7/2 stem with the folded weight layout (one k-block per kh, contiguous 128-byte gathers)."""
+    from byol_b200 import ops
+    n, h, w = shape
+    g = torch.Generator().manual_seed(23)
+    x = R.bf16_round(torch.rand(n, h, w, 3, generator=g))
+    wt = R.bf16_round(torch.randn(64, 3, 7, 7, generator=g) / 12.0)
+    xp = torch.zeros(n, h, w, 8)
+    xp[..., :3] = x
+    wf = ops.prep_weight_fold(wt.to(cuda))
+    assert wf.shape == (64, 448)
+    ref = R.conv_fprop_ref(x, wt, 2, 3)
+    stats = torch.zeros(128, device=cuda)
+    y = ops.conv_fprop(xp.to(cuda, torch.bfloat16), wf, 7, 7, 2, 3, stats=stats)
+    torch.cuda.synchronize()
+    assert_close("stem_fold", y, ref, atol=1e-2 * float(ref.abs().max()), rtol=0)
+    yr = y.float().cpu().reshape(-1, 64)
+    assert_close("stem_fold_stats", stats[:64], yr.sum(0), atol=1e-3 * yr.abs().sum(0).max().item(), rtol=0)
+
+
 def test_conv_dgrad_parity_with_residual(cuda):
     """BasicBlock-style strided 3x3 dgrad with the residual gradient added in the epilogue (parity mode)."""
     from byol_b200 import ops

@@ -34,6 +34,26 @@ def test_bn_forward(cuda, m, c):
     assert_close("bn_running_var", rvd, 0.9 * rv + 0.1 * var * m / (m - 1), atol=1e-5, rtol=1e-4)
 
 
+def test_bn_finalize_lanes_matches_sequential(cuda):
+    """The multi-lane finalize equals four sequential single-lane calls (coefficients and running statistics)."""
+    from byol_b200 import ops
+    c, m, L = 256, 500, 4
+    g = torch.Generator().manual_seed(11)
+    stats = (torch.rand(L * 2 * c, generator=g) * 100).to(cuda)
+    stats.view(L, 2, c)[:, 1] += 200.0     # make E[x^2] >= E[x]^2
+    gam = [torch.rand(c, generator=g).to(cuda) + 0.5 for _ in range(L)]
+    bet = [torch.randn(c, generator=g).to(cuda) for _ in range(L)]
+    rm1, rv1 = torch.zeros(c, device=cuda), torch.ones(c, device=cuda)
+    rm2, rv2 = rm1.clone(), rv1.clone()
+    co1 = torch.empty(L, 4, c, device=cuda)
+    co2 = torch.empty(L, 4, c, device=cuda)
+    for l in range(L):
+        ops.bn_finalize(stats[l * 2 * c:(l + 1) * 2 * c], m, gam[l], bet[l], rm1, rv1, 0.1, 1e-5, co1[l])
+    ops.bn_finalize_lanes(stats, m, gam, bet, rm2, rv2, 0.1, 1e-5, co2)
+    torch.cuda.synchronize()
+    assert torch.equal(co1, co2) and torch.equal(rm1, rm2) and torch.equal(rv1, rv2)
+
+
 def test_bn_apply_residual(cuda):
     from byol_b200 import ops
     m, c = 200, 128
