@@ -63,6 +63,20 @@ class _Weights(object):
             self.wd = [None] * len(units)
 
 
+class _Pool(object):
+    """Bump allocator over one fp32 tensor (one memset / allocation per pass instead of one per layer)."""
+
+    def __init__(self, n, device, zero):
+        self.buf = torch.zeros(n, dtype=F32, device=device) if zero else torch.empty(n, dtype=F32, device=device)
+        self.off = 0
+
+    def take(self, n):
+        t = self.buf[self.off:self.off + n]
+        self.off += n
+        assert self.off <= self.buf.numel()
+        return t
+
+
 class Engine(object):
     def __init__(self, model):
         self.model = model
@@ -186,6 +200,7 @@ class Engine(object):
         self.cls = self._unit(model.linear_classifier, None, "classifier")
         self.cls.want_dgrad = False
         self.bn_modules = [u.bn for u in self.units if u.bn is not None]
+        self.bn_channels = sum(u.cout for u in self.units if u.bn is not None)
         self.sync = any(isinstance(b, nn.SyncBatchNorm) for b in self.bn_modules)
         self.w_online = _Weights(self.units, self.device, True)
         self.w_target = _Weights(self.units, self.device, False)
@@ -209,7 +224,7 @@ class Engine(object):
     def _conv_bn(self, u, xs, lanes, train):
         """raw conv/linear outputs + BN coefficients [scale, shift, mean, invstd] per lane."""
         L, C = len(lanes), u.cout
-        stats = torch.zeros(L * 2 * C, dtype=F32, device=self.device) if train else None
+        stats = self._zpool.take(L * 2 * C) if train else None
         ys = []
         for i, (flat, wset, _) in enumerate(lanes):
             st = stats[i * 2 * C:(i + 1) * 2 * C] if train else None
@@ -220,7 +235,7 @@ class Engine(object):
             else:
                 y = ops.conv_fprop(x, wset.wf[u.idx], u.k, u.k, u.stride, u.pad, stats=st)
             ys.append(y)
-        coeffs = torch.empty((L, 4, C), dtype=F32, device=self.device)
+        coeffs = self._cpool.take(L * 4 * C).view(L, 4, C)
         bn = u.bn
         if train:
             rows = ys[0].numel() // C
@@ -291,6 +306,8 @@ class Engine(object):
         Returns per lane (representation fp32, projection fp32, prediction fp32)."""
         L = len(lanes)
         st = self.stem
+        self._zpool = _Pool(L * 2 * self.bn_channels, self.device, zero=True) if train else None
+        self._cpool = _Pool(L * 4 * self.bn_channels, self.device, zero=False)
         x8 = [ops.nchw_to_nhwc8(a) for a in augs]
         y0, c0 = self._conv_bn(st, x8, lanes, train)
         a0 = [self._apply(y0[i], c0[i], True) for i in range(L)]
@@ -329,7 +346,7 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------
     def _bn_bwd(self, u, gs, ys, cs, mask_mode, acts=None, want_dz=False):
         L, C = len(gs), u.cout
-        s12 = torch.zeros(L * 2 * C, dtype=F32, device=self.device)
+        s12 = self._bpool.take(L * 2 * C)
         for i in range(L):
             ops.bn_bwd_reduce(gs[i].view(-1, C), ys[i].view(-1, C), cs[i], s12[i * 2 * C:(i + 1) * 2 * C], mask_mode,
                               act=None if acts is None else acts[i].view(-1, C))
@@ -418,6 +435,7 @@ class Engine(object):
         """saved: per online view the dict filled by forward_lanes; d_*: fp32 grads (or None) of the outputs."""
         self.notify_backward()
         L = len(saved)
+        self._bpool = _Pool(L * 2 * self.bn_channels, self.device, zero=True)
         zero = lambda ref: torch.zeros_like(ref)
         # predictor
         if all(d is None for d in d_preds) and all(d is None for d in d_projs) and all(d is None for d in d_reps):

@@ -11,6 +11,7 @@ import pytest
 import torch
 
 from oracle import byol_oracle as O
+from byol_b200 import engine as E
 
 pytestmark = pytest.mark.gpu
 
@@ -67,6 +68,7 @@ def test_blocks_teacher_forced(cuda, arch, rep):
         gg = torch.Generator().manual_seed(100 + bi)
         g_out = torch.randn(S["out"].shape, generator=gg).to(torch.bfloat16)
         eng.grad.zero_()
+        eng._bpool = E._Pool(2 * eng.bn_channels, eng.device, zero=True)
         g_in = eng._block_bwd(blk, [S], [g_out.cuda()])[0]
         torch.cuda.synchronize()
         x = _nchw(S["x"]).requires_grad_(True)
@@ -86,6 +88,7 @@ def test_blocks_teacher_forced(cuda, arch, rep):
     gg = torch.Generator().manual_seed(99)
     g_pool = torch.randn(pool_out.shape, generator=gg).to(torch.bfloat16)
     eng.grad.zero_()
+    eng._bpool = E._Pool(2 * eng.bn_channels, eng.device, zero=True)
     from byol_b200 import ops
     n, h, w, c = saved["a0_shape"]
     g0 = ops.maxpool_bwd(g_pool.cuda(), saved["pool_idx"], h, w, eng.pool_k, eng.pool_s, eng.pool_p)

@@ -103,7 +103,8 @@ def _run_steps(cuda, arch, rep, b, r, steps, seed, lr, total, out_tol, golden=No
                 if out_tol is not None:
                     # encoder gradients pass through every BatchNorm/ReLU mask of the net: statistical agreement
                     # only (tests/test_gpu_blocks.py is the exact, teacher-forced gate); heads must agree tightly
-                    assert ck > (0.995 if k.startswith(("predictor", "linear_classifier")) else 0.8), k
+                    lim = 0.995 if k.startswith(("predictor", "linear_classifier")) else (0.8 if s == 0 else 0.5)
+                    assert ck > lim, k
         th = model._engine.theta
         upd_c = _cos(th.cpu() - prev_theta, oracle.flat_params() - prev_oracle)
         print("  update cosine %.5f" % upd_c)
