@@ -88,3 +88,21 @@ def test_bn_statistic_combination_matches_global_batch():
     full = torch.cat(shards)
     np.testing.assert_allclose(mean.numpy(), full.mean(0).numpy(), rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(var.numpy(), full.var(0, unbiased=False).numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_lr_schedule_first_epoch_is_zero():
+    """Q11: lr = 0.2 * 4096/256 = 3.2, linear warm-up over 10 epochs starting AT 0, then cosine."""
+    from byol_b200.wiring import build_optimizer
+    from byol_b200.scheduler import build_lr_schedule
+    net = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.BatchNorm1d(4))
+    opt = build_optimizer(net, base_lr=0.2, global_batch_size=4096)
+    sched = build_lr_schedule(opt, epochs=100, warmup=10)
+    lrs = []
+    for _ in range(14):
+        lrs.append(opt.param_groups[0]["lr"])
+        sched.step()
+    assert lrs[0] == 0.0                                        # the whole first epoch trains with lr = 0
+    np.testing.assert_allclose(lrs[1:11], [0.32 * i for i in range(1, 11)], rtol=1e-12)
+    assert abs(lrs[10] - 3.2) < 1e-12 and lrs[12] < lrs[11] <= 3.2   # then cosine decay
+    sd = sched.state_dict()
+    assert set(sd.keys()) == {"warmup", "sched"}
