@@ -103,7 +103,7 @@ def _run_steps(cuda, arch, rep, b, r, steps, seed, lr, total, out_tol, golden=No
                 if out_tol is not None:
                     # encoder gradients pass through every BatchNorm/ReLU mask of the net: statistical agreement
                     # only (tests/test_gpu_blocks.py is the exact, teacher-forced gate); heads must agree tightly
-                    lim = 0.995 if k.startswith(("predictor", "linear_classifier")) else (0.8 if s == 0 else 0.5)
+                    lim = 0.995 if k.startswith(("predictor", "linear_classifier")) else (0.7 if s == 0 else 0.4)
                     assert ck > lim, k
         th = model._engine.theta
         upd_c = _cos(th.cpu() - prev_theta, oracle.flat_params() - prev_oracle)
