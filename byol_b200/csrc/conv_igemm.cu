@@ -895,6 +895,13 @@ static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64
   return 0;
 }
 
+// conv_patch.cu
+bool patch_conv_applicable(int H, int W, int C, int Ndim, int KH, int KW, int stride, int pad, int out_fp32,
+                           const float* bias, int64_t src_elems);
+int patch_conv_launch(const void* src, const void* wt, void* dst, const void* resid, float* col_sum, float* col_sqsum,
+                      int Nimg, int H, int W, int C, int Ndim, int ldw, int ldc, int flip, int relu, int sms,
+                      cudaStream_t stream);
+
 static int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -947,6 +954,11 @@ extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const
   const int64_t M64 = (int64_t)Nimg * Ho * Wo;
   BYOL_CHECK_ARG(M64 > 0 && M64 < (1ll << 31), "byol_conv_igemm: M out of range");
   BYOL_CHECK_ARG((int64_t)Nimg * Hs * Ws * C < (1ll << 40), "byol_conv_igemm: src too large");
+  // 3x3 / stride 1 / pad 1 (fprop and its dgrad): shared-memory patch reuse instead of a 9x re-gather
+  if (!force_gather && Hs == Ho && Ws == Wo && ldw >= 9 * C &&
+      patch_conv_applicable(Hs, Ws, C, Ndim, KH, KW, stride, pad, out_fp32, bias, (int64_t)Nimg * Hs * Ws * C))
+    return patch_conv_launch(src, wt, dst, resid, col_sum, col_sqsum, Nimg, Hs, Ws, C, Ndim, ldw, ldc, mode, relu,
+                             sm_count(), stream);
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   p.src = (const bf16*)src;
