@@ -28,7 +28,8 @@ struct PatchParams {
   int Nimg, H, W, C;    // input == output spatial size (stride 1, pad 1)
   int Ndim, ldc;
   int Wp, TH, HB;       // W + 2, output rows per tile, tiles per image = ceil(H / TH)
-  int tiles_n, num_tiles;
+  int tiles_n, num_tiles;   // num_tiles counts PAIR tiles: two consecutive M-tiles x one N-tile
+  int num_mt;               // number of M-tiles = Nimg * HB
   int nchunks;          // C / 64
   int flip;             // 0: fprop tap shift kh*Wp + kw ; 1: dgrad (2-kh)*Wp + (2-kw)
   int relu;
@@ -36,7 +37,7 @@ struct PatchParams {
 };
 
 static constexpr int P_PATCH_SLOT = 32768;   // bytes per patch slot (>= 128 * (128 + 2*Wp + 2))
-static constexpr int P_PSTAGES = 2;
+static constexpr int P_PSTAGES = 2;          // patch GROUP stages; a group = the patches of the (up to) 2 M-tiles of a pair
 static constexpr int P_BSTAGES = 4;
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
@@ -53,7 +54,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_con
                      const PatchParams p) {
   constexpr int B_STAGE = BN * 128;
   constexpr int PATCH_OFF = 0;
-  constexpr int B_OFF = P_PSTAGES * P_PATCH_SLOT;
+  constexpr int B_OFF = P_PSTAGES * 2 * P_PATCH_SLOT;
   constexpr int STAGE_OUT_OFF = B_OFF + P_BSTAGES * B_STAGE;   // 4 warps x [32 rows][64 B]
   constexpr int BAR_OFF = STAGE_OUT_OFF + 4 * 2048;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -81,7 +82,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_con
     tma_prefetch_desc(&tmapB);
   }
   if (warp == 4) {
-    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_alloc(tmem_slot, 4 * BN);     // 2 accumulator stages x 2 M-tiles of a pair
     tmem_relinquish();
   }
   tc_fence_before_sync();
@@ -100,9 +101,8 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_con
     int stat_n0 = -1;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
       const int tile_n = tile % p.tiles_n;
-      const int mt = tile / p.tiles_n;
-      const int n = mt / p.HB;
-      const int h0 = (mt - n * p.HB) * p.TH;
+      const int mt0 = (tile / p.tiles_n) * 2;
+      const int npair = (mt0 + 1 < p.num_mt) ? 2 : 1;
       const int n0 = tile_n * BN;
       if (do_stats && stat_n0 != n0) {
         if (stat_n0 >= 0) {
@@ -117,6 +117,13 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_con
         }
         stat_n0 = n0;
       }
+      const int acc = local & 1;
+      mbar_wait(&tfull[acc], (uint32_t)((local >> 1) & 1));
+      tc_fence_after_sync();
+      for (int jp = 0; jp < npair; ++jp) {
+      const int mt = mt0 + jp;
+      const int n = mt / p.HB;
+      const int h0 = (mt - n * p.HB) * p.TH;
       // GEMM row -> output pixel (rows with ocol >= W, orow >= TH or beyond the image are garbage)
       const int ml = warp * 32 + lane;
       const int orow = ml / p.Wp;
@@ -124,16 +131,13 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_con
       const bool rvalid = orow < p.TH && ocol < p.W && (h0 + orow) < p.H;
       const int64_t opix = ((int64_t)n * p.H + h0 + orow) * p.W + ocol;
       const uint32_t vmask = __ballot_sync(0xffffffffu, rvalid);
-      const int acc = local & 1;
-      mbar_wait(&tfull[acc], (uint32_t)((local >> 1) & 1));
-      tc_fence_after_sync();
 #pragma unroll
       for (int ci = 0; ci < BN / 32; ++ci) {
         const int c0 = ci * 32;
         uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((acc * 2 + jp) * BN + c0), r);
         tmem_ld_wait();
-        if (ci == BN / 32 - 1) {
+        if (ci == BN / 32 - 1 && jp == npair - 1) {
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -206,6 +210,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_con
           csq[ci] += s2;
         }
       }
+      }   // jp
     }
     if (do_stats && stat_n0 >= 0) {
 #pragma unroll
@@ -223,26 +228,32 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_con
       int pit = 0, bit = 0, local = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
         const int acc = local & 1;
+        const int mt0 = (tile / p.tiles_n) * 2;
+        const int npair = (mt0 + 1 < p.num_mt) ? 2 : 1;
         mbar_wait(&tempty[acc], (uint32_t)(((local >> 1) & 1) ^ 1));
         tc_fence_after_sync();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int cc = 0; cc < p.nchunks; ++cc, ++pit) {
           const int ps = pit % P_PSTAGES;
           mbar_wait(&pfull[ps], (uint32_t)((pit / P_PSTAGES) & 1));
-          const uint32_t patch = smem_u32(smemP + ps * P_PATCH_SLOT);
+          const uint32_t patch = smem_u32(smemP + ps * 2 * P_PATCH_SLOT);
           for (int tap = 0; tap < 9; ++tap, ++bit) {
             const int bs = bit % P_BSTAGES;
             mbar_wait(&bfull[bs], (uint32_t)((bit / P_BSTAGES) & 1));
             tc_fence_after_sync();
             const int kh = tap / 3, kw = tap - kh * 3;
             const int shift = p.flip ? ((2 - kh) * p.Wp + (2 - kw)) : (kh * p.Wp + kw);
-            // shifted window over the swizzled patch image: start address only 128-byte aligned, base_offset 0
-            const uint64_t adesc = make_smem_desc_sw128(patch + (uint32_t)shift * 128u, 16, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smemB + bs * B_STAGE), 16, 1024);
+            // the same weight tile multiplies the patches of both M-tiles of the pair
+            for (int jp = 0; jp < npair; ++jp) {
+              // shifted window over the swizzled patch image: start address only 128-byte aligned, base_offset 0
+              const uint64_t adesc =
+                  make_smem_desc_sw128(patch + (uint32_t)jp * P_PATCH_SLOT + (uint32_t)shift * 128u, 16, 1024);
+              const uint32_t tmem_d = tmem_base + (uint32_t)((acc * 2 + jp) * BN);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                        (uint32_t)((cc | tap | k) != 0));
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                          (uint32_t)((cc | tap | k) != 0));
+            }
             umma_commit(&bempty[bs]);
           }
           umma_commit(&pempty[ps]);
@@ -262,13 +273,17 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_con
       auto issue_patch = [&](int g) {
         const int tile = blockIdx.x + (g / p.nchunks) * gridDim.x;
         const int cc = g % p.nchunks;
-        const int mt = tile / p.tiles_n;
-        const int n = mt / p.HB;
-        const int h0 = (mt - n * p.HB) * p.TH;
+        const int mt0 = (tile / p.tiles_n) * 2;
+        const int npair = (mt0 + 1 < p.num_mt) ? 2 : 1;
         const int ps = g % P_PSTAGES;
         mbar_wait(&pempty[ps], (uint32_t)(((g / P_PSTAGES) & 1) ^ 1));
-        mbar_arrive_expect_tx(&pfull[ps], p.patch_bytes);
-        tma_load_4d(smem_u32(smemP + ps * P_PATCH_SLOT), &tmapX, &pfull[ps], cc * 64, -1, h0 - 1, n);
+        mbar_arrive_expect_tx(&pfull[ps], p.patch_bytes * (uint32_t)npair);
+        for (int jp = 0; jp < npair; ++jp) {
+          const int mt = mt0 + jp;
+          const int n = mt / p.HB;
+          const int h0 = (mt - n * p.HB) * p.TH;
+          tma_load_4d(smem_u32(smemP + (ps * 2 + jp) * P_PATCH_SLOT), &tmapX, &pfull[ps], cc * 64, -1, h0 - 1, n);
+        }
       };
       int bit = 0;
       if (total > 0) issue_patch(0);
@@ -292,7 +307,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_con
   __syncthreads();
   if (warp == 4) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, 4 * BN);
   }
 }
 
@@ -316,7 +331,7 @@ static PFN_encodeTiled patch_encode_fn() {
 template <int BN>
 static int launch_patch(const CUtensorMap& tx, const CUtensorMap& tb, const PatchParams& p, int sms,
                         cudaStream_t stream) {
-  constexpr int SMEM = P_PSTAGES * P_PATCH_SLOT + P_BSTAGES * BN * 128 + 4 * 2048 + 256 + 1024;
+  constexpr int SMEM = P_PSTAGES * 2 * P_PATCH_SLOT + P_BSTAGES * BN * 128 + 4 * 2048 + 256 + 1024;
   auto kern = conv3x3_patch_kernel<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -364,7 +379,8 @@ int patch_conv_launch(const void* src, const void* wt, void* dst, const void* re
   p.HB = (H + p.TH - 1) / p.TH;
   const int BN = Ndim > 64 ? 128 : 64;
   p.tiles_n = (Ndim + BN - 1) / BN;
-  p.num_tiles = Nimg * p.HB * p.tiles_n;
+  p.num_mt = Nimg * p.HB;
+  p.num_tiles = ((p.num_mt + 1) / 2) * p.tiles_n;
   p.nchunks = C / 64;
   p.flip = flip;
   p.relu = relu;
