@@ -67,6 +67,44 @@ __global__ void prep_weight_fold_kernel(const float* __restrict__ w, bf16* __res
   }
 }
 
+// All conv / linear weights of one parameter set in ONE launch.  desc[u] = {src_off, dstf_off, dstd_off (-1: none),
+// Cout, Cin, Cpad, taps, fold(KH,KW packed as KH*16+KW or 0)} (int64 each); blockIdx.y = unit, grid-stride in x.
+__global__ void prep_weights_multi_kernel(const float* __restrict__ flat, bf16* __restrict__ pool_f,
+                                          bf16* __restrict__ pool_d, const int64_t* __restrict__ desc) {
+  const int64_t* d = desc + (int64_t)blockIdx.y * 8;
+  const float* w = flat + d[0];
+  bf16* wf = pool_f + d[1];
+  bf16* wd = d[2] >= 0 ? pool_d + d[2] : nullptr;
+  const int Cout = (int)d[3], Cin = (int)d[4], Cpad = (int)d[5], taps = (int)d[6], fold = (int)d[7];
+  if (fold) {
+    const int KH = fold >> 4, KW = fold & 15;
+    const int64_t total = (int64_t)Cout * KH * 64;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int c = (int)(i & 7);
+      const int kw = (int)((i >> 3) & 7);
+      const int64_t t = i >> 6;
+      const int kh = (int)(t % KH);
+      const int co = (int)(t / KH);
+      float v = 0.f;
+      if (c < Cin && kw < KW) v = __ldg(w + (((int64_t)co * Cin + c) * KH + kh) * KW + kw);
+      wf[i] = __float2bfloat16_rn(v);
+    }
+    return;
+  }
+  const int64_t total = (int64_t)Cout * taps * Cpad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cpad);
+    const int64_t t = i / Cpad;
+    const int tap = (int)(t % taps);
+    const int co = (int)(t / taps);
+    float v = 0.f;
+    if (c < Cin) v = __ldg(w + ((int64_t)co * Cin + c) * taps + tap);
+    const bf16 b = __float2bfloat16_rn(v);
+    wf[i] = b;
+    if (wd != nullptr && c < Cin) wd[((int64_t)c * taps + tap) * Cout + co] = b;
+  }
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16_rn(x[i]);
@@ -135,16 +173,14 @@ __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* _
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    for (int kh = 0; kh < k; ++kh) {
-      const int th = ih + p - kh;
-      if (th < 0 || th % s != 0) continue;
-      const int oh = th / s;
-      if (oh >= Ho) continue;
-      for (int kw = 0; kw < k; ++kw) {
-        const int tw = iw + p - kw;
-        if (tw < 0 || tw % s != 0) continue;
-        const int ow = tw / s;
-        if (ow >= Wo) continue;
+    // only window offsets kh == (ih + p) mod s (step s) can have produced this pixel: <= ceil(k/s)^2 candidates,
+    // no division in the loops
+    for (int kh = (ih + p) % s; kh < k; kh += s) {
+      const int oh = (ih + p - kh) / s;
+      if (oh < 0 || oh >= Ho) continue;
+      for (int kw = (iw + p) % s; kw < k; kw += s) {
+        const int ow = (iw + p - kw) / s;
+        if (ow < 0 || ow >= Wo) continue;
         const int64_t o = (((int64_t)n * Ho + oh) * Wo + ow) * groups + g;
         const uint2 pk = __ldg(reinterpret_cast<const uint2*>(idx) + o);
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(dy) + o);
@@ -273,6 +309,15 @@ extern "C" int byol_prep_weight_fold(const float* w, void* w_fprop, int Cout, in
   const int64_t total = (int64_t)Cout * KH * 64;
   prep_weight_fold_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, (bf16*)w_fprop, Cout, Cin, KH, KW);
   return check_launch("prep_weight_fold_kernel");
+}
+
+// desc: device array [num_units][8] int64 (see prep_weights_multi_kernel); pool_d may be null if no entry needs it
+extern "C" int byol_prep_weights_multi(const float* flat, void* pool_f, void* pool_d, const int64_t* desc,
+                                       int num_units, cudaStream_t stream) {
+  BYOL_CHECK_ARG(flat && pool_f && desc && num_units > 0, "byol_prep_weights_multi: bad args");
+  dim3 grid(32, num_units);
+  prep_weights_multi_kernel<<<grid, 256, 0, stream>>>(flat, (bf16*)pool_f, (bf16*)pool_d, desc);
+  return check_launch("prep_weights_multi_kernel");
 }
 
 extern "C" int byol_cast_f32_bf16(const float* x, void* y, int64_t n, cudaStream_t stream) {

@@ -42,11 +42,14 @@ class _Weights(object):
     def __init__(self, units, device, want_dgrad):
         nf = sum(u.cout * u.kcols for u in units)
         self.pool_f = torch.empty(nf, dtype=BF16, device=device)
+        self.pool_d = None
         self.wf, self.wd = [], []
+        self.off_f, self.off_d = [], []
         off = 0
         for u in units:
             n = u.cout * u.kcols
             self.wf.append(self.pool_f[off:off + n].view(u.cout, u.kcols))
+            self.off_f.append(off)
             off += n
         if want_dgrad:
             nd = sum(u.cin * u.k * u.k * u.cout for u in units if u.want_dgrad)
@@ -56,11 +59,24 @@ class _Weights(object):
                 if u.want_dgrad:
                     n = u.cin * u.k * u.k * u.cout
                     self.wd.append(self.pool_d[off:off + n].view(u.cin, u.k * u.k * u.cout))
+                    self.off_d.append(off)
                     off += n
                 else:
                     self.wd.append(None)
+                    self.off_d.append(-1)
         else:
             self.wd = [None] * len(units)
+            self.off_d = [-1] * len(units)
+        # descriptor tables for the one-launch weight conversion (with and without the dgrad layouts)
+        rows_d, rows_n = [], []
+        for u in units:
+            fold = (u.k * 16 + u.k) if u.fold else 0
+            base = [u.w_off, self.off_f[u.idx], -1, u.cout, u.cin, u.cpad, u.k * u.k, fold]
+            rows_n.append(list(base))
+            base[2] = self.off_d[u.idx] if (u.want_dgrad and not u.fold) else -1
+            rows_d.append(base)
+        self.desc_with_dgrad = torch.tensor(rows_d, dtype=torch.int64, device=device)
+        self.desc_fprop_only = torch.tensor(rows_n, dtype=torch.int64, device=device)
 
 
 class _Pool(object):
@@ -210,13 +226,9 @@ class Engine(object):
         return comm.world_size()
 
     def prep_weights(self, flat, wset, want_dgrad):
-        for u in self.units:
-            w = flat[u.w_off:u.w_off + u.w_numel].view(u.cout, u.cin, u.k, u.k)
-            if u.fold:
-                ops.prep_weight_fold(w, out_f=wset.wf[u.idx])
-            else:
-                ops.prep_weight(w, cpad=u.cpad, want_dgrad=want_dgrad and u.want_dgrad, out_f=wset.wf[u.idx],
-                                out_d=wset.wd[u.idx])
+        """fp32 master (flat vector) -> bf16 tensor-core layouts of every conv / linear, one launch."""
+        desc = wset.desc_with_dgrad if (want_dgrad and wset.pool_d is not None) else wset.desc_fprop_only
+        ops.prep_weights_multi(flat, wset.pool_f, wset.pool_d, desc)
 
     # ------------------------------------------------------------------------------------------
     # forward building blocks (lists are per lane)
@@ -308,7 +320,12 @@ class Engine(object):
         st = self.stem
         self._zpool = _Pool(L * 2 * self.bn_channels, self.device, zero=True) if train else None
         self._cpool = _Pool(L * 4 * self.bn_channels, self.device, zero=False)
-        x8 = [ops.nchw_to_nhwc8(a) for a in augs]
+        conv = {}
+        x8 = []
+        for a in augs:     # online and target lanes of one view share the converted input
+            if id(a) not in conv:
+                conv[id(a)] = ops.nchw_to_nhwc8(a)
+            x8.append(conv[id(a)])
         y0, c0 = self._conv_bn(st, x8, lanes, train)
         a0 = [self._apply(y0[i], c0[i], True) for i in range(L)]
         xs = []

@@ -81,6 +81,12 @@ def prep_weight_fold(w, out_f=None):
     return out_f
 
 
+def prep_weights_multi(flat, pool_f, pool_d, desc):
+    """All weights of one parameter set (flat fp32 vector) -> bf16 tensor-core layouts, one launch."""
+    check(lib.byol_prep_weights_multi(_ptr(flat), _ptr(pool_f), _ptr(pool_d), _ptr(desc), desc.shape[0], _stream()),
+          "byol_prep_weights_multi")
+
+
 def cast_bf16(x, out=None):
     _chk(x, F32, "x")
     if out is None:

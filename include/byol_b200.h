@@ -82,6 +82,10 @@ int byol_prep_weight(const float* w, void* w_fprop, void* w_dgrad, int Cout, int
                      byol_stream_t stream);
 /* stem layout ([Cout][KH*64], column = kh*64 + kw*8 + c) selected by byol_conv_igemm when C == 8 and ldw == KH*64 */
 int byol_prep_weight_fold(const float* w, void* w_fprop, int Cout, int Cin, int KH, int KW, byol_stream_t stream);
+/* every conv / linear weight of one parameter set in one launch; desc: device int64 [num_units][8] =
+ * {src offset in flat, fprop offset in pool_f, dgrad offset in pool_d or -1, Cout, Cin, Cpad, taps, fold (KH*16+KW or 0)} */
+int byol_prep_weights_multi(const float* flat, void* pool_f, void* pool_d, const int64_t* desc, int num_units,
+                            byol_stream_t stream);
 int byol_cast_f32_bf16(const float* x, void* y, int64_t n, byol_stream_t stream);
 int byol_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, int k, int s, int p,
                      byol_stream_t stream);
