@@ -276,8 +276,10 @@ def main_b200(args):
     l0 = _lib.launch_count[0]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         stats = wiring.train_step(net, opt, aug1, aug2, labels)
+    host_ms = 1000.0 * (time.perf_counter() - t_host0) / args.steps   # Python time to ENQUEUE one step
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -370,6 +372,7 @@ def main_b200(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "loss": loss_val, "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+            "host_enqueue_ms_per_step": host_ms,
         }
         print(json.dumps(line))
     if world > 1:

@@ -355,7 +355,7 @@ bool patch_conv_applicable(int H, int W, int C, int Ndim, int KH, int KW, int st
   const int Wp = W + 2;
   // measured on B200 (512 images): faster than the gather kernel at 56x56 (1.4x) and 28x28, slower at 14x14 and
   // below, where few of the 128 tile rows are valid and the gather kernel's two CTAs per SM hide more latency
-  if (Wp > 128 || W < 24) return false;
+  if (Wp > 128 || W < 12) return false;
   const int TH = 128 / Wp;
   if (128 * (128 + 2 * Wp + 2) > P_PATCH_SLOT) return false;
   if (128 * Wp * (TH + 2) > P_PATCH_SLOT) return false;
