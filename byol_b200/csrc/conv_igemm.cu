@@ -902,6 +902,10 @@ int patch_conv_launch(const void* src, const void* wt, void* dst, const void* re
                       int Nimg, int H, int W, int C, int Ndim, int ldw, int ldc, int flip, int relu, int sms,
                       cudaStream_t stream);
 
+bool patch_wgrad_applicable(int H, int W, int C, int Cin_real, int Cout, int KH, int KW, int stride, int pad);
+int patch_wgrad_launch(const void* x, const void* dy, float* dw, int Nimg, int H, int W, int C, int Cout, int sms,
+                       cudaStream_t stream);
+
 static int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -1055,6 +1059,9 @@ extern "C" int byol_conv_wgrad(const void* src, const void* dy, float* dw, int N
   BYOL_CHECK_ARG(Cin_real <= C, "byol_conv_wgrad: Cin_real > C");
   const int64_t M64 = (int64_t)Nimg * Ho * Wo;
   BYOL_CHECK_ARG(M64 > 0 && M64 < (1ll << 31), "byol_conv_wgrad: M out of range");
+  // 3x3 / stride 1 / pad 1: shifted-window kernel over TMA patches (no gather)
+  if (!force_gather && Hs == Ho && Ws == Wo && patch_wgrad_applicable(Hs, Ws, C, Cin_real, Cout, KH, KW, stride, pad))
+    return patch_wgrad_launch(src, dy, dw, Nimg, Hs, Ws, C, Cout, sm_count(), stream);
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.src = (const bf16*)src;

@@ -411,3 +411,222 @@ int patch_conv_launch(const void* src, const void* wt, void* dst, const void* re
 }
 
 }  // namespace byol
+
+// =================================================================================================
+// 3x3 / stride-1 / pad-1 WGRAD with the same shifted-window trick.
+//   dW[co, ci, kh, kw] += sum_pixels dY[pix, co] * X[pix + (kh-1, kw-1), ci]
+// Per M-tile (TH image rows, GEMM K rows = orow*(W+2)+ocol, 128 of them):
+//   A = dY tile  [128 pixel rows][128 co]  MN-major, TMA box {64 co, W+2, TH, 1}: the two garbage columns and rows
+//       beyond the image are out-of-bounds -> ZERO, so garbage rows contribute nothing
+//   B = X patch  [(TH+2)*(W+2) pixel rows][64*NB ci] MN-major; tap (kh,kw) = the same image shifted by kh*(W+2)+kw rows
+//   D[128 co][kw*64*NB + ci] for the three taps of ONE kh row per CTA, accumulated in TMEM over the CTA's range of
+//   M-tiles, then added to the fp32 gradient with L2 reductions.
+// Rows of the smem slots that TMA never writes (beyond the boxes) are zeroed once, so stale shared memory can not
+// inject Inf/NaN through the zero rows of A.
+// =================================================================================================
+namespace byol {
+
+struct WPatchParams {
+  float* dw;            // [Cout][Cin][3][3] fp32
+  int Nimg, H, W, C, Cout;
+  int Wp, TH, HB, num_mt;
+  int co_tiles, ci_groups;
+  int splits, mt_per_split;
+  uint32_t patch_bytes; // 128 * Wp * (TH + 2)
+  uint32_t dy_bytes;    // 128 * Wp * TH
+};
+
+static constexpr int WP_STAGES = 2;
+
+template <int NB>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapDY,
+                           const WPatchParams p) {
+  constexpr int X_STAGE = NB * P_PATCH_SLOT;
+  constexpr int DY_STAGE = 2 * 16384;
+  constexpr int DY_OFF = WP_STAGES * X_STAGE;
+  constexpr int BAR_OFF = DY_OFF + WP_STAGES * DY_STAGE;
+  constexpr int NCOLS = 3 * 64 * NB;
+  constexpr int TMEM_COLS = NCOLS <= 256 ? 256 : 512;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smemX = smem;
+  uint8_t* smemDY = smem + DY_OFF;
+  uint64_t* full_bar = (uint64_t*)(smem + BAR_OFF);
+  uint64_t* empty_bar = full_bar + WP_STAGES;
+  uint64_t* accum_bar = empty_bar + WP_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  int bid = blockIdx.x;
+  const int kh = bid % 3;               bid /= 3;
+  const int cig = bid % p.ci_groups;    bid /= p.ci_groups;
+  const int tile_co = bid % p.co_tiles; bid /= p.co_tiles;
+  const int split = bid;
+  const int co0 = tile_co * 128;
+  const int ci0 = cig * 64 * NB;
+  const int mt_begin = split * p.mt_per_split;
+  int mt_end = mt_begin + p.mt_per_split;
+  if (mt_end > p.num_mt) mt_end = p.num_mt;
+  const int ntiles = mt_end - mt_begin;   // host guarantees >= 1
+
+  // zero every operand slot once (see header comment)
+  for (int i = threadIdx.x; i < BAR_OFF / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < WP_STAGES; ++s) { mbar_init(&full_bar[s], 1u); mbar_init(&empty_bar[s], 1u); }
+    mbar_init(accum_bar, 1u);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmapX);
+    tma_prefetch_desc(&tmapDY);
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5) {
+    if (lane == 0) {
+      for (int it = 0; it < ntiles; ++it) {
+        const int mt = mt_begin + it;
+        const int n = mt / p.HB;
+        const int h0 = (mt - n * p.HB) * p.TH;
+        const int s = it % WP_STAGES;
+        mbar_wait(&empty_bar[s], (uint32_t)(((it / WP_STAGES) & 1) ^ 1));
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)NB * p.patch_bytes + 2u * p.dy_bytes);
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+          tma_load_4d(smem_u32(smemX + s * X_STAGE + c * P_PATCH_SLOT), &tmapX, &full_bar[s], ci0 + 64 * c, -1, h0 - 1, n);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          tma_load_4d(smem_u32(smemDY + s * DY_STAGE + j * 16384), &tmapDY, &full_bar[s], co0 + 64 * j, 0, h0, n);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(1u, 128, 64 * NB, 1u, 1u);   // both operands MN-major
+      for (int it = 0; it < ntiles; ++it) {
+        const int s = it % WP_STAGES;
+        mbar_wait(&full_bar[s], (uint32_t)((it / WP_STAGES) & 1));
+        tc_fence_after_sync();
+        const uint32_t a_base = smem_u32(smemDY + s * DY_STAGE);
+        const uint32_t x_base = smem_u32(smemX + s * X_STAGE);
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const uint32_t shift = (uint32_t)(kh * p.Wp + kw) * 128u;
+          // A: 2 co chunks 16384 B apart; B: NB ci chunks P_PATCH_SLOT apart; 8-row groups 1024 B apart
+          const uint64_t adesc = make_smem_desc_sw128(a_base, 16384, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(x_base + shift, P_PATCH_SLOT, 1024);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // 16 pixel rows = 2048 bytes per step
+            umma_bf16(tmem_base + (uint32_t)(kw * 64 * NB), adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k),
+                      idesc, (uint32_t)((it | k) != 0));
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: TMEM -> L2 reductions into dW[co][ci][kh][kw] ----------------
+    mbar_wait(accum_bar, 0);
+    tc_fence_after_sync();
+    const int co = co0 + warp * 32 + lane;
+    const bool covalid = co < p.Cout;
+#pragma unroll 1
+    for (int c0 = 0; c0 < NCOLS; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      if (!covalid) continue;
+      const int kw = c0 / (64 * NB);
+      const int cib = ci0 + (c0 - kw * 64 * NB);
+      float* gp = p.dw + ((int64_t)co * p.C) * 9 + kh * 3 + kw;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (cib + j < p.C) atomicAdd(gp + (int64_t)(cib + j) * 9, __uint_as_float(r[j]));
+    }
+    tc_fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int NB>
+static int launch_wpatch(const CUtensorMap& tx, const CUtensorMap& ty, const WPatchParams& p, int grid,
+                         cudaStream_t stream) {
+  constexpr int SMEM = WP_STAGES * (NB * P_PATCH_SLOT + 2 * 16384) + 256 + 1024;
+  auto kern = conv3x3_wgrad_patch_kernel<NB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(conv3x3_wgrad_patch) failed: %s", cudaGetErrorString(e));
+      return -2;
+    }
+    attr_set = true;
+  }
+  kern<<<grid, 192, SMEM, stream>>>(tx, ty, p);
+  return check_launch("conv3x3_wgrad_patch_kernel");
+}
+
+bool patch_wgrad_applicable(int H, int W, int C, int Cin_real, int Cout, int KH, int KW, int stride, int pad) {
+  if (KH != 3 || KW != 3 || stride != 1 || pad != 1) return false;
+  if (C % 64 != 0 || C != Cin_real || Cout % 8 != 0) return false;
+  const int Wp = W + 2;
+  if (Wp > 128 || W < 12) return false;
+  if (128 * (128 + 2 * Wp + 2) > P_PATCH_SLOT) return false;
+  (void)H;
+  return true;
+}
+
+// x: NHWC [Nimg,H,W,C]; dy: [Nimg,H,W,Cout]; dw: fp32 [Cout][C][3][3] (accumulated)
+int patch_wgrad_launch(const void* x, const void* dy, float* dw, int Nimg, int H, int W, int C, int Cout, int sms,
+                       cudaStream_t stream) {
+  PFN_encodeTiled fn = patch_encode_fn();
+  if (fn == nullptr) { set_last_error("cuTensorMapEncodeTiled entry point unavailable"); return -3; }
+  WPatchParams p;
+  memset(&p, 0, sizeof(p));
+  p.dw = dw; p.Nimg = Nimg; p.H = H; p.W = W; p.C = C; p.Cout = Cout;
+  p.Wp = W + 2;
+  p.TH = 128 / p.Wp;
+  if (p.TH > H) p.TH = H;
+  p.HB = (H + p.TH - 1) / p.TH;
+  p.num_mt = Nimg * p.HB;
+  const int NB = (C % 128 == 0) ? 2 : 1;
+  p.co_tiles = (Cout + 127) / 128;
+  p.ci_groups = C / (64 * NB);
+  const int base = p.co_tiles * p.ci_groups * 3;
+  int splits = sms / base;
+  if (splits < 1) splits = 1;
+  if (splits > p.num_mt) splits = p.num_mt;
+  p.mt_per_split = (p.num_mt + splits - 1) / splits;
+  p.splits = (p.num_mt + p.mt_per_split - 1) / p.mt_per_split;
+  p.patch_bytes = 128u * (uint32_t)p.Wp * (uint32_t)(p.TH + 2);
+  p.dy_bytes = 128u * (uint32_t)p.Wp * (uint32_t)p.TH;
+  CUtensorMap tx, ty;
+  for (int which = 0; which < 2; ++which) {
+    const int ch = which == 0 ? C : Cout;
+    cuuint64_t dims[4] = {(cuuint64_t)ch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
+    cuuint64_t strides[3] = {(cuuint64_t)ch * 2, (cuuint64_t)W * ch * 2, (cuuint64_t)H * W * ch * 2};
+    cuuint32_t box[4] = {64u, (cuuint32_t)p.Wp, (cuuint32_t)(which == 0 ? p.TH + 2 : p.TH), 1u};
+    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult r = fn(which == 0 ? &tx : &ty, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                    const_cast<void*>(which == 0 ? x : dy), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_last_error("patch wgrad: tensor map encode failed (%d)", (int)r); return -3; }
+  }
+  const int grid = base * p.splits;
+  return NB == 2 ? launch_wpatch<2>(tx, ty, p, grid, stream) : launch_wpatch<1>(tx, ty, p, grid, stream);
+}
+
+}  // namespace byol
