@@ -23,6 +23,9 @@ CONV_CASES = [
     ("3x3_patch_28", 2, 28, 28, 128, 128, 128, 3, 1, 1),        # auto -> patch-reuse kernel (W >= 24)
     ("3x3_patch_56_64", 1, 56, 56, 64, 64, 64, 3, 1, 1),
     ("3x3_patch_30x26", 3, 30, 26, 64, 64, 256, 3, 1, 1),       # ragged: H not a multiple of the tile rows
+    ("3x3_patch_48", 1, 48, 48, 64, 64, 64, 3, 1, 1),           # 384x384 input geometries (ResNet stages 2-4)
+    ("3x3_patch_24", 3, 24, 24, 128, 128, 128, 3, 1, 1),
+    ("3x3_patch_12", 5, 12, 12, 256, 256, 256, 3, 1, 1),
     ("3x3s2_128_128", 1, 28, 28, 128, 128, 128, 3, 2, 1),
     ("1x1s2_256_512", 1, 28, 28, 256, 256, 512, 1, 2, 0),
     ("3x3_512_512_7", 3, 7, 7, 512, 512, 512, 3, 1, 1),
