@@ -99,6 +99,9 @@ class Engine(object):
         self.device = None
         self.ready = False
         self._bwd_cb_queued = False
+        self._side_stream = None
+        self._side_used = False
+        self.overlap_wgrad = True
 
     # ------------------------------------------------------------------------------------------
     # flat buffers
@@ -218,6 +221,7 @@ class Engine(object):
         self.bn_modules = [u.bn for u in self.units if u.bn is not None]
         self.bn_channels = sum(u.cout for u in self.units if u.bn is not None)
         self.sync = any(isinstance(b, nn.SyncBatchNorm) for b in self.bn_modules)
+        self._side_stream = torch.cuda.Stream(device=self.device) if self.overlap_wgrad else None
         self.w_online = _Weights(self.units, self.device, True)
         self.w_target = _Weights(self.units, self.device, False)
         self.ready = True
@@ -388,12 +392,36 @@ class Engine(object):
         return dys, dzs
 
     def _wgrad(self, u, xs, dys):
+        """dW += dY^T * im2col(X) on the side stream: the weight-gradient GEMMs only feed the flat gradient buffer, so
+        they overlap with the HBM-bound BatchNorm-backward kernels of the next layer on the main stream."""
         dw = self._gview(u.w_off, u.w_numel).view(u.cout, u.cin, u.k, u.k)
+        main = torch.cuda.current_stream()
+        side = self._side_stream
+        if side is None:
+            self._launch_wgrad(u, xs, dys, dw)
+            return
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            self._launch_wgrad(u, xs, dys, dw)
+        for t in list(xs) + list(dys):
+            t.record_stream(side)      # keep the caching allocator from recycling operands the side stream still reads
+        self._side_used = True
+
+    def _launch_wgrad(self, u, xs, dys, dw):
         for x, dy in zip(xs, dys):
             if u.kind == "linear":
                 ops.conv_wgrad(x.view(x.shape[0], 1, 1, -1), dy.view(dy.shape[0], 1, 1, -1), dw, 1, 1, 1, 0)
             else:
                 ops.conv_wgrad(x, dy, dw, u.k, u.k, u.stride, u.pad)
+
+    def _join_side_stream(self):
+        if self._side_stream is not None and self._side_used:
+            ev = torch.cuda.Event()
+            ev.record(self._side_stream)
+            torch.cuda.current_stream().wait_event(ev)
+            self._side_used = False
 
     def _dgrad(self, u, dys, in_shapes, resids=None):
         wd = self.w_online.wd[u.idx]
@@ -470,6 +498,7 @@ class Engine(object):
         if head_in is not None:
             rep_g = self._mlp_bwd(self.mlps[0], [s["head"] for s in saved], head_in)
         if rep_g is None and all(d is None for d in d_reps):
+            self._join_side_stream()
             return
         gs = []
         for i, s in enumerate(saved):
@@ -484,6 +513,7 @@ class Engine(object):
             g0.append(ops.maxpool_bwd(gs[i], s["pool_idx"], h, w, self.pool_k, self.pool_s, self.pool_p))
         dy0, _ = self._bn_bwd(self.stem, g0, [s["y0"] for s in saved], [s["c0"] for s in saved], 1)
         self._wgrad(self.stem, [s["x8"] for s in saved], dy0)
+        self._join_side_stream()
 
     # classifier (stop-grad input; main.py:250-252)
     def classifier_forward(self, rep_cat_b):
@@ -497,6 +527,7 @@ class Engine(object):
         d = d_logits.contiguous()
         ops.col_sum(d, self._gview(u.b_off, u.cout))
         self._wgrad(u, [rep_cat_b], [ops.cast_bf16(d)])
+        self._join_side_stream()
 
     # ------------------------------------------------------------------------------------------
     # DDP: one flat gradient all-reduce (mean) when the backward pass finishes (main.py:440-443, 617)
@@ -509,4 +540,5 @@ class Engine(object):
 
     def _finish_backward(self):
         self._bwd_cb_queued = False
+        self._join_side_stream()
         comm.allreduce_mean_(self.grad)
