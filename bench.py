@@ -274,6 +274,7 @@ def main_b200(args):
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count[0]
+    ms0 = torch.cuda.memory_stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     t_host0 = time.perf_counter()
@@ -284,6 +285,10 @@ def main_b200(args):
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = (_lib.launch_count[0] - l0) // args.steps
+    ms1 = torch.cuda.memory_stats()
+    alloc_info = {"cudaMalloc_calls_in_timed_region": ms1.get("num_device_alloc", 0) - ms0.get("num_device_alloc", 0),
+                  "cudaFree_calls_in_timed_region": ms1.get("num_device_free", 0) - ms0.get("num_device_free", 0),
+                  "alloc_retries": ms1.get("num_alloc_retries", 0), "reserved_gb": torch.cuda.memory_reserved() / 1e9}
     clocks = sampler.stop() if rank == 0 else None
     loss_val = float(stats["loss_mean"].item())
     value = args.steps * gb / (ms / 1000.0)
@@ -372,7 +377,7 @@ def main_b200(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "loss": loss_val, "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
-            "host_enqueue_ms_per_step": host_ms,
+            "host_enqueue_ms_per_step": host_ms, "allocator": alloc_info,
         }
         print(json.dumps(line))
     if world > 1:

@@ -247,9 +247,9 @@ bn_bwd_apply_fixed_kernel(const bf16* __restrict__ g, const bf16* __restrict__ x
                           float* __restrict__ dbeta) {
   const int groups = C >> 3;
   if (blockIdx.x == 0 && dgamma != nullptr) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      dgamma[c] += s2_local[c];
-      dbeta[c] += s1_local[c];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {   // atomics: the two online views may run concurrently
+      atomicAdd(dgamma + c, s2_local[c]);
+      atomicAdd(dbeta + c, s1_local[c]);
     }
   }
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -361,9 +361,9 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ g, const bf16* __re
   const int groups = C >> 3;
   if (blockIdx.x == 0 && dgamma != nullptr) {
     // parameter gradients come from the rank-LOCAL sums (SyncBatchNorm.backward, _functions.py:122-170)
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      dgamma[c] += s2_local[c];
-      dbeta[c] += s1_local[c];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {   // atomics: the two online views may run concurrently
+      atomicAdd(dgamma + c, s2_local[c]);
+      atomicAdd(dbeta + c, s1_local[c]);
     }
   }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {

@@ -101,7 +101,13 @@ class Engine(object):
         self._bwd_cb_queued = False
         self._side_stream = None
         self._side_used = False
+        self._side_refs = []
         self.overlap_wgrad = True
+        self.multi_stream = True
+        self._fwd_streams = None
+        self._bwd_streams = None
+        self._fin_events = None
+        self._group_order = 0
 
     # ------------------------------------------------------------------------------------------
     # flat buffers
@@ -222,6 +228,10 @@ class Engine(object):
         self.bn_channels = sum(u.cout for u in self.units if u.bn is not None)
         self.sync = any(isinstance(b, nn.SyncBatchNorm) for b in self.bn_modules)
         self._side_stream = torch.cuda.Stream(device=self.device) if self.overlap_wgrad else None
+        # the same two streams serve the forward lane pairs and the backward views: every extra stream is an extra
+        # caching-allocator pool, and pools do not share their cached blocks
+        self._fwd_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        self._bwd_streams = self._fwd_streams
         self.w_online = _Weights(self.units, self.device, True)
         self.w_target = _Weights(self.units, self.device, False)
         self.ready = True
@@ -259,9 +269,15 @@ class Engine(object):
             if self.sync and self.world() > 1:
                 comm.allreduce_sum_(stats)
                 count = rows * self.world()
+            fin = self._fin_events
+            if fin is not None and self._group_order == 1:
+                torch.cuda.current_stream().wait_event(fin[u.idx])     # running stats: online pair first
             ops.bn_finalize_lanes(stats, count, [flat[u.g_off:u.g_off + C] for flat, _, _ in lanes],
                                   [flat[u.beta_off:u.beta_off + C] for flat, _, _ in lanes], bn.running_mean,
                                   bn.running_var, bn.momentum, bn.eps, coeffs)
+            if fin is not None and self._group_order == 0:
+                fin[u.idx] = torch.cuda.Event()
+                fin[u.idx].record(torch.cuda.current_stream())
         else:
             for i, (flat, _, _) in enumerate(lanes):
                 ops.bn_eval_coeffs(flat[u.g_off:u.g_off + C], flat[u.beta_off:u.beta_off + C], bn.running_mean,
@@ -319,17 +335,56 @@ class Engine(object):
 
     def forward_lanes(self, augs, lanes, train, rep_bf16_out=None):
         """augs: fp32 NCHW inputs per lane; lanes: (flat params, weight set, saved dict or None) per lane.
-        Returns per lane (representation fp32, projection fp32, prediction fp32)."""
+        Returns per lane (representation fp32, projection fp32, prediction fp32).
+
+        With four lanes (online x2, target x2) the two pairs run on two CUDA streams forked from / joined into the
+        caller's stream: the HBM-bound BatchNorm kernels of one pair overlap the tensor-core convolutions of the
+        other.  BN running statistics keep the reference's per-layer update order (online pair before target pair)
+        through one event per layer."""
         L = len(lanes)
-        st = self.stem
-        self._zpool = _Pool(L * 2 * self.bn_channels, self.device, zero=True) if train else None
-        self._cpool = _Pool(L * 4 * self.bn_channels, self.device, zero=False)
+        main = torch.cuda.current_stream()
         conv = {}
         x8 = []
         for a in augs:     # online and target lanes of one view share the converted input
             if id(a) not in conv:
                 conv[id(a)] = ops.nchw_to_nhwc8(a)
             x8.append(conv[id(a)])
+        if rep_bf16_out is None:
+            rep_bf16_out = [None] * L
+        two = self.multi_stream and L == 4
+        groups = [(list(range(0, 2)), self._fwd_streams[0]), (list(range(2, 4)), self._fwd_streams[1])] if two \
+            else [(list(range(L)), main)]
+        self._fin_events = {} if (two and train) else None
+        results = [None] * L
+        reps_b_all = [None] * L
+        if two:
+            ev = torch.cuda.Event()
+            ev.record(main)
+        for order, (idxs, stream) in enumerate(groups):
+            if two:
+                stream.wait_event(ev)
+            self._group_order = order
+            with torch.cuda.stream(stream):
+                res, rb = self._forward_group([x8[i] for i in idxs], [lanes[i] for i in idxs], train,
+                                              [rep_bf16_out[i] for i in idxs])
+            for j, i in enumerate(idxs):
+                results[i], reps_b_all[i] = res[j], rb[j]
+        if two:
+            for _, stream in groups:
+                e2 = torch.cuda.Event()
+                e2.record(stream)
+                main.wait_event(e2)
+        self._fin_events = None
+        self._group_order = 0
+        if train:
+            torch._foreach_add_([b.num_batches_tracked for b in self.bn_modules], L)
+        return results, reps_b_all
+
+    def _forward_group(self, x8, lanes, train, rep_bf16_out):
+        L = len(lanes)
+        st = self.stem
+        self._zpool = _Pool(L * 2 * self.bn_channels, self.device, zero=True) if train else None
+        self._cpool = _Pool(L * 4 * self.bn_channels, self.device, zero=False)
         y0, c0 = self._conv_bn(st, x8, lanes, train)
         a0 = [self._apply(y0[i], c0[i], True) for i in range(L)]
         xs = []
@@ -344,9 +399,7 @@ class Engine(object):
             xs = self._block_fwd(b, xs, lanes, train)
         reps_f, reps_b = [], []
         for i in range(L):
-            out_b = None
-            if rep_bf16_out is not None and rep_bf16_out[i] is not None:
-                out_b = rep_bf16_out[i]
+            out_b = rep_bf16_out[i]
             n, h, w, c = xs[i].shape
             yf = torch.empty((n, c), dtype=F32, device=self.device)
             yb = out_b if out_b is not None else torch.empty((n, c), dtype=BF16, device=self.device)
@@ -358,8 +411,6 @@ class Engine(object):
                 lanes[i][2]["final_shape"] = (n, h, w, c)
         proj_f, proj_b = self._mlp_fwd(self.mlps[0], reps_b, lanes, train, "head")
         pred_f, _ = self._mlp_fwd(self.mlps[1], proj_b, lanes, train, "pred")
-        if train:
-            torch._foreach_add_([b.num_batches_tracked for b in self.bn_modules], L)
         return [(reps_f[i], proj_f[i], pred_f[i]) for i in range(L)], reps_b
 
     # ------------------------------------------------------------------------------------------
@@ -405,8 +456,9 @@ class Engine(object):
         side.wait_event(ev)
         with torch.cuda.stream(side):
             self._launch_wgrad(u, xs, dys, dw)
-        for t in list(xs) + list(dys):
-            t.record_stream(side)      # keep the caching allocator from recycling operands the side stream still reads
+        # keep the operands alive until the launching stream has joined the side stream (no record_stream: that would
+        # add an allocator event per tensor); after the join, reuse by the owning stream is ordered behind the reads
+        self._side_refs.append((xs, dys))
         self._side_used = True
 
     def _launch_wgrad(self, u, xs, dys, dw):
@@ -422,6 +474,7 @@ class Engine(object):
             ev.record(self._side_stream)
             torch.cuda.current_stream().wait_event(ev)
             self._side_used = False
+            self._side_refs = []
 
     def _dgrad(self, u, dys, in_shapes, resids=None):
         wd = self.w_online.wd[u.idx]
@@ -477,8 +530,29 @@ class Engine(object):
         return [ops.linear_dgrad(dhs[i], self.w_online.wd[l1.idx]) for i in range(L)]
 
     def backward_online(self, saved, d_reps, d_projs, d_preds):
-        """saved: per online view the dict filled by forward_lanes; d_*: fp32 grads (or None) of the outputs."""
+        """Backward of the online views.  Each view runs on its own CUDA stream (forked from / joined into the
+        caller's stream) so that one view's HBM-bound BatchNorm-backward kernels overlap the other's GEMMs; both
+        accumulate into the same flat gradient buffer with atomic reductions."""
         self.notify_backward()
+        L = len(saved)
+        main = torch.cuda.current_stream()
+        if not (self.multi_stream and L == 2):
+            self._backward_group(saved, d_reps, d_projs, d_preds)
+            return
+        ev = torch.cuda.Event()
+        ev.record(main)
+        for i in range(L):
+            stream = self._bwd_streams[i]
+            stream.wait_event(ev)
+            with torch.cuda.stream(stream):
+                self._backward_group([saved[i]], [d_reps[i]], [d_projs[i]], [d_preds[i]])
+        for i in range(L):
+            e2 = torch.cuda.Event()
+            e2.record(self._bwd_streams[i])
+            main.wait_event(e2)
+
+    def _backward_group(self, saved, d_reps, d_projs, d_preds):
+        """saved: per online view the dict filled by forward_lanes; d_*: fp32 grads (or None) of the outputs."""
         L = len(saved)
         self._bpool = _Pool(L * 2 * self.bn_channels, self.device, zero=True)
         zero = lambda ref: torch.zeros_like(ref)
