@@ -43,6 +43,8 @@ _SIGNATURES = {
     "byol_prep_weights_multi": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "byol_cast_f32_bf16": [c_void_p, c_void_p, c_int64, c_void_p],
     "byol_maxpool_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "byol_bn_relu_maxpool_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                 c_int, c_int, c_void_p],
     "byol_maxpool_bwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "byol_avgpool_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "byol_avgpool_bwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],

@@ -158,6 +158,62 @@ __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict_
   }
 }
 
+// Stem fusion: y = maxpool(relu(x*scale + shift)) without materialising the normalised map.  Candidates are rounded
+// to bf16 before the comparison, so values AND argmax indices equal bn_apply followed by maxpool_fwd bit for bit.
+__global__ void bn_relu_maxpool_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ scale,
+                                           const float* __restrict__ shift, bf16* __restrict__ y,
+                                           uint8_t* __restrict__ idx, int N, int H, int W, int C, int Ho, int Wo,
+                                           int k, int s, int p) {
+  const int groups = C >> 3;
+  const int64_t total = (int64_t)N * Ho * Wo * groups;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    int64_t t = i / groups;
+    const int ow = (int)(t % Wo); t /= Wo;
+    const int oh = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float sc[8], sh[8], best[8];
+    int bi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sc[e] = __ldg(scale + g * 8 + e);
+      sh[e] = __ldg(shift + g * 8 + e);
+      best[e] = -INFINITY;
+      bi[e] = 0;
+    }
+    for (int kh = 0; kh < k; ++kh) {
+      const int ih = oh * s - p + kh;
+      if (ih < 0 || ih >= H) continue;
+      for (int kw = 0; kw < k; ++kw) {
+        const int iw = ow * s - p + kw;
+        if (iw < 0 || iw >= W) continue;
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)n * H + ih) * W + iw) * C + g * 8));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __bfloat1622float2(h[e]);
+          const float a0 = __bfloat162float(__float2bfloat16_rn(fmaxf(f.x * sc[2 * e] + sh[2 * e], 0.f)));
+          const float a1 = __bfloat162float(__float2bfloat16_rn(fmaxf(f.y * sc[2 * e + 1] + sh[2 * e + 1], 0.f)));
+          if (a0 > best[2 * e] || a0 != a0) { best[2 * e] = a0; bi[2 * e] = kh * k + kw; }
+          if (a1 > best[2 * e + 1] || a1 != a1) { best[2 * e + 1] = a1; bi[2 * e + 1] = kh * k + kw; }
+        }
+      }
+    }
+    uint4 q;
+    q.x = pack_bf16x2(best[0], best[1]);
+    q.y = pack_bf16x2(best[2], best[3]);
+    q.z = pack_bf16x2(best[4], best[5]);
+    q.w = pack_bf16x2(best[6], best[7]);
+    reinterpret_cast<uint4*>(y)[i] = q;
+    if (idx != nullptr) {
+      uint2 pk;
+      pk.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+      pk.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+      reinterpret_cast<uint2*>(idx)[i] = pk;
+    }
+  }
+}
+
 // dx[n, ih, iw, c] = sum over output windows (oh, ow) containing (ih, iw) whose saved argmax is this position
 __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ idx,
                                    bf16* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo, int k, int s,
@@ -334,6 +390,17 @@ extern "C" int byol_maxpool_fwd(const void* x, void* y, void* idx, int N, int H,
   maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const bf16*)x, (bf16*)y, (uint8_t*)idx, N, H, W, C,
                                                               Ho, Wo, k, s, p);
   return check_launch("maxpool_fwd_kernel");
+}
+
+// y = maxpool_kxk/s/p(relu(x*scale + shift)), idx as byol_maxpool_fwd (stem: BN-apply + ReLU + pool in one pass)
+extern "C" int byol_bn_relu_maxpool_fwd(const void* x, const float* scale, const float* shift, void* y, void* idx,
+                                        int N, int H, int W, int C, int k, int s, int p, cudaStream_t stream) {
+  BYOL_CHECK_ARG(x && scale && shift && y && C % 8 == 0 && k * k <= 255, "byol_bn_relu_maxpool_fwd: bad args");
+  const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
+  const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+  bn_relu_maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const bf16*)x, scale, shift, (bf16*)y,
+                                                                      (uint8_t*)idx, N, H, W, C, Ho, Wo, k, s, p);
+  return check_launch("bn_relu_maxpool_fwd_kernel");
 }
 
 extern "C" int byol_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, int k, int s,

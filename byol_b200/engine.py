@@ -386,15 +386,15 @@ class Engine(object):
         self._zpool = _Pool(L * 2 * self.bn_channels, self.device, zero=True) if train else None
         self._cpool = _Pool(L * 4 * self.bn_channels, self.device, zero=False)
         y0, c0 = self._conv_bn(st, x8, lanes, train)
-        a0 = [self._apply(y0[i], c0[i], True) for i in range(L)]
         xs = []
         for i, (_, _, saved) in enumerate(lanes):
-            p, idx = ops.maxpool_fwd(a0[i], self.pool_k, self.pool_s, self.pool_p, want_idx=saved is not None)
+            # stem: BN-apply + ReLU + max-pool fused (the normalised 112x112 map is never written)
+            p, idx = ops.bn_relu_maxpool_fwd(y0[i], c0[i][0], c0[i][1], self.pool_k, self.pool_s, self.pool_p,
+                                             want_idx=saved is not None)
             xs.append(p)
             if saved is not None:
-                saved.update({"x8": x8[i], "y0": y0[i], "c0": c0[i], "a0_shape": tuple(a0[i].shape), "pool_idx": idx,
+                saved.update({"x8": x8[i], "y0": y0[i], "c0": c0[i], "a0_shape": tuple(y0[i].shape), "pool_idx": idx,
                               "blocks": []})
-        del a0
         for b in self.blocks:
             xs = self._block_fwd(b, xs, lanes, train)
         reps_f, reps_b = [], []

@@ -255,6 +255,18 @@ def maxpool_fwd(x, k=3, s=2, p=1, want_idx=True):
     return y, idx
 
 
+def bn_relu_maxpool_fwd(x, scale, shift, k=3, s=2, p=1, want_idx=True):
+    """maxpool(relu(x*scale + shift)) in one pass (stem); bit-identical to bn_apply(relu) + maxpool_fwd."""
+    _chk(x, BF16, "x")
+    n, h, w, c = x.shape
+    ho, wo = conv_out_size(h, k, s, p), conv_out_size(w, k, s, p)
+    y = torch.empty((n, ho, wo, c), dtype=BF16, device=x.device)
+    idx = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=x.device) if want_idx else None
+    check(lib.byol_bn_relu_maxpool_fwd(_ptr(x), _ptr(scale), _ptr(shift), _ptr(y), _ptr(idx), n, h, w, c, k, s, p,
+                                       _stream()), "byol_bn_relu_maxpool_fwd")
+    return y, idx
+
+
 def maxpool_bwd(dy, idx, h, w, k=3, s=2, p=1):
     _chk(dy, BF16, "dy")
     n, ho, wo, c = dy.shape

@@ -89,6 +89,9 @@ int byol_prep_weights_multi(const float* flat, void* pool_f, void* pool_d, const
 int byol_cast_f32_bf16(const float* x, void* y, int64_t n, byol_stream_t stream);
 int byol_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, int k, int s, int p,
                      byol_stream_t stream);
+/* stem fusion: y = maxpool(relu(x*scale + shift)); values and argmax indices equal bn_apply + maxpool_fwd exactly */
+int byol_bn_relu_maxpool_fwd(const void* x, const float* scale, const float* shift, void* y, void* idx, int N, int H,
+                             int W, int C, int k, int s, int p, byol_stream_t stream);
 int byol_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, int k, int s, int p,
                      byol_stream_t stream);
 int byol_avgpool_fwd(const void* x, float* y_f32, void* y_bf16, int N, int HW, int C, byol_stream_t stream);

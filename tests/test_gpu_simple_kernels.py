@@ -165,6 +165,19 @@ def test_pooling(cuda):
     assert_close("avgpool_bwd", dxa, ((gb + gf) / 49)[:, None, None, :].expand(5, 7, 7, 64), atol=1e-3, rtol=1e-2)
 
 
+def test_fused_stem_pool_is_bit_identical(cuda):
+    """bn_relu_maxpool_fwd == bn_apply(relu) -> maxpool_fwd, values and argmax indices."""
+    from byol_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    x = R.bf16_round(torch.randn(3, 18, 22, 64, generator=g)).to(cuda, BF)
+    sc, sh = (torch.rand(64, generator=g) + 0.5).to(cuda), torch.randn(64, generator=g).to(cuda)
+    a = ops.bn_apply(x.view(-1, 64), sc, sh, relu=True).view(3, 18, 22, 64)
+    y1, i1 = ops.maxpool_fwd(a)
+    y2, i2 = ops.bn_relu_maxpool_fwd(x, sc, sh)
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2) and torch.equal(i1, i2)
+
+
 def _loss_ref(q1, q2, z1, z2):
     # /root/reference/objective.py:6-25 restated (Frobenius norms of the whole matrices, no per-row normalisation)
     def reg(x, y):
