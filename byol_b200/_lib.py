@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbyol_b200.so")
+# BYOL_B200_LIB: A/B timing of an older build of the same C ABI (tools/time_cases.py); the product path never sets it
+LIB_PATH = os.environ.get("BYOL_B200_LIB") or os.path.join(_HERE, "libbyol_b200.so")
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int
@@ -18,7 +19,8 @@ c_double = ctypes.c_double
 
 # name -> argtypes (all functions return int status unless listed in _SPECIAL)
 _SIGNATURES = {
-    "byol_conv_igemm": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,  # src wt dst resid bias col_sum col_sqsum
+    "byol_conv_igemm": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,                      # src wt dst resid resid_mask
+                        c_void_p, c_void_p, c_void_p,                                          # bias col_sum col_sqsum
                         c_int, c_int, c_int, c_int, c_int, c_int, c_int,                      # Nimg Hs Ws C Ho Wo Ndim
                         c_int, c_int, c_int, c_int, c_int, c_int, c_int,                      # KH KW stride pad mode ldw ldc
                         c_int, c_int, c_int, c_void_p],                                        # out_fp32 relu force_gather stream
@@ -30,8 +32,8 @@ _SIGNATURES = {
     "byol_bn_finalize_lanes": [c_void_p, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_int, c_void_p],
     "byol_bn_eval_coeffs": [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p],
-    "byol_bn_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                      c_int, c_void_p],
+    "byol_bn_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                      c_int, c_int, c_int, c_void_p],
     "byol_bn_bwd_reduce": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                            c_int, c_int, c_void_p],
     "byol_bn_bwd_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -151,12 +151,21 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return q;
 }
 
+// bit e = (o[e] > 0): the ReLU mask of one 8-channel vector (one byte per vector, same linear order as the data)
+__device__ __forceinline__ uint8_t positive_bits(const float* o) {
+  uint32_t b = 0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) b |= (o[e] > 0.f ? 1u : 0u) << e;
+  return (uint8_t)b;
+}
+
 // y = act(x*scale + shift + residual);  residual = resid (rscale == null) or resid*rscale + rshift
 // Each thread handles one 8-channel vector; grid-stride over M*C/8 vectors.
 __global__ void bn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ scale,
                                 const float* __restrict__ shift, const bf16* __restrict__ resid,
                                 const float* __restrict__ rscale, const float* __restrict__ rshift,
-                                bf16* __restrict__ y, float* __restrict__ y_f32, int64_t nvec, int C, int relu) {
+                                bf16* __restrict__ y, float* __restrict__ y_f32, uint8_t* __restrict__ mask_out,
+                                int64_t nvec, int C, int relu) {
   const int groups = C >> 3;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(i % groups);
@@ -187,6 +196,7 @@ __global__ void bn_apply_kernel(const bf16* __restrict__ x, const float* __restr
       for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
     }
     if (y != nullptr) reinterpret_cast<uint4*>(y)[i] = pack8(o);
+    if (mask_out != nullptr) mask_out[i] = positive_bits(o);
     if (y_f32 != nullptr) {
       reinterpret_cast<float4*>(y_f32)[2 * i] = make_float4(o[0], o[1], o[2], o[3]);
       reinterpret_cast<float4*>(y_f32)[2 * i + 1] = make_float4(o[4], o[5], o[6], o[7]);
@@ -201,7 +211,8 @@ template <bool RESID, bool RAFFINE>
 __global__ void __launch_bounds__(256)
 bn_apply_fixed_kernel(const bf16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                       const bf16* __restrict__ resid, const float* __restrict__ rscale,
-                      const float* __restrict__ rshift, bf16* __restrict__ y, int64_t nvec, int C, int relu) {
+                      const float* __restrict__ rshift, bf16* __restrict__ y, uint8_t* __restrict__ mask_out,
+                      int64_t nvec, int C, int relu) {
   const int groups = C >> 3;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int g = (int)(tid % groups);
@@ -230,6 +241,7 @@ bn_apply_fixed_kernel(const bf16* __restrict__ x, const float* __restrict__ scal
       for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
     }
     reinterpret_cast<uint4*>(y)[i] = pack8(o);
+    if (mask_out != nullptr) mask_out[i] = positive_bits(o);
   }
 }
 
@@ -271,7 +283,11 @@ bn_bwd_apply_fixed_kernel(const bf16* __restrict__ g, const bf16* __restrict__ x
     float gv[8], xv[8], o[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(g) + i), gv);
     unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), xv);
-    if (MASK == 2) {
+    if (MASK == 3) {
+      const uint32_t mb = __ldg(reinterpret_cast<const uint8_t*>(act) + i);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gv[e] = ((mb >> e) & 1u) ? gv[e] : 0.f;
+    } else if (MASK == 2) {
       float av[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(act) + i), av);
 #pragma unroll
@@ -287,7 +303,8 @@ bn_bwd_apply_fixed_kernel(const bf16* __restrict__ g, const bf16* __restrict__ x
   }
 }
 
-// mask_mode: 0 = none (dz = g), 1 = ReLU mask recomputed from x (x*scale+shift > 0), 2 = mask from act > 0
+// mask_mode: 0 = none (dz = g), 1 = ReLU mask recomputed from x (x*scale+shift > 0), 2 = mask from act > 0,
+// 3 = mask bits written by bn_apply (`act` = uint8 [M*C/8], bit e of byte i = element 8*i + e)
 template <int MASK>
 __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ x,
                                      const bf16* __restrict__ act, const float* __restrict__ scale,
@@ -320,7 +337,11 @@ __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __r
       float gv[8], xv[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(g) + off), gv);
       unpack8(__ldg(reinterpret_cast<const uint4*>(x) + off), xv);
-      if (MASK == 2) {
+      if (MASK == 3) {
+        const uint32_t mb = __ldg(reinterpret_cast<const uint8_t*>(act) + off);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gv[e] = ((mb >> e) & 1u) ? gv[e] : 0.f;
+      } else if (MASK == 2) {
         float av[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(act) + off), av);
 #pragma unroll
@@ -371,7 +392,11 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ g, const bf16* __re
     float gv[8], xv[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(g) + i), gv);
     unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), xv);
-    if (MASK == 2) {
+    if (MASK == 3) {
+      const uint32_t mb = __ldg(reinterpret_cast<const uint8_t*>(act) + i);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gv[e] = ((mb >> e) & 1u) ? gv[e] : 0.f;
+    } else if (MASK == 2) {
       float av[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(act) + i), av);
 #pragma unroll
@@ -478,23 +503,24 @@ extern "C" int byol_bn_eval_coeffs(const float* gamma, const float* beta, const 
 }
 
 extern "C" int byol_bn_apply(const void* x, const float* scale, const float* shift, const void* resid,
-                             const float* rscale, const float* rshift, void* y, float* y_f32, int M, int C,
-                             int relu, cudaStream_t stream) {
+                             const float* rscale, const float* rshift, void* y, float* y_f32, void* mask_out,
+                             int M, int C, int relu, cudaStream_t stream) {
   BYOL_CHECK_ARG(x && scale && shift && (y || y_f32) && M > 0 && C % 8 == 0, "byol_bn_apply: bad args");
+  uint8_t* mo = (uint8_t*)mask_out;
   const int64_t nvec = (int64_t)M * C / 8;
   const int fg = (y != nullptr && y_f32 == nullptr) ? fixed_grid(nvec, C / 8) : 0;
   if (fg > 0) {
     const bf16 *xp = (const bf16*)x, *rp = (const bf16*)resid;
     if (resid == nullptr)
-      bn_apply_fixed_kernel<false, false><<<fg, 256, 0, stream>>>(xp, scale, shift, rp, rscale, rshift, (bf16*)y, nvec, C, relu);
+      bn_apply_fixed_kernel<false, false><<<fg, 256, 0, stream>>>(xp, scale, shift, rp, rscale, rshift, (bf16*)y, mo, nvec, C, relu);
     else if (rscale == nullptr)
-      bn_apply_fixed_kernel<true, false><<<fg, 256, 0, stream>>>(xp, scale, shift, rp, rscale, rshift, (bf16*)y, nvec, C, relu);
+      bn_apply_fixed_kernel<true, false><<<fg, 256, 0, stream>>>(xp, scale, shift, rp, rscale, rshift, (bf16*)y, mo, nvec, C, relu);
     else
-      bn_apply_fixed_kernel<true, true><<<fg, 256, 0, stream>>>(xp, scale, shift, rp, rscale, rshift, (bf16*)y, nvec, C, relu);
+      bn_apply_fixed_kernel<true, true><<<fg, 256, 0, stream>>>(xp, scale, shift, rp, rscale, rshift, (bf16*)y, mo, nvec, C, relu);
     return check_launch("bn_apply_fixed_kernel");
   }
   bn_apply_kernel<<<grid_for(nvec, 256), 256, 0, stream>>>((const bf16*)x, scale, shift, (const bf16*)resid, rscale,
-                                                           rshift, (bf16*)y, y_f32, nvec, C, relu);
+                                                           rshift, (bf16*)y, y_f32, mo, nvec, C, relu);
   return check_launch("bn_apply_kernel");
 }
 
@@ -503,7 +529,8 @@ extern "C" int byol_bn_bwd_reduce(const void* g, const void* x, const void* act,
                                   const float* shift, const float* mean, const float* invstd, float* s12, int M,
                                   int C, int mask_mode, cudaStream_t stream) {
   BYOL_CHECK_ARG(g && x && mean && invstd && s12 && M > 0 && C % 8 == 0, "byol_bn_bwd_reduce: bad args");
-  BYOL_CHECK_ARG(mask_mode != 2 || act, "byol_bn_bwd_reduce: mask_mode 2 needs act");
+  BYOL_CHECK_ARG(mask_mode >= 0 && mask_mode <= 3, "byol_bn_bwd_reduce: bad mask_mode %d", mask_mode);
+  BYOL_CHECK_ARG(mask_mode < 2 || act, "byol_bn_bwd_reduce: mask_mode 2/3 needs act");
   BYOL_CHECK_ARG(mask_mode != 1 || (scale && shift), "byol_bn_bwd_reduce: mask_mode 1 needs scale/shift");
   int rows_per_block = (M + 148 * 8 - 1) / (148 * 8);
   if (rows_per_block < 32) rows_per_block = 32;
@@ -513,8 +540,10 @@ extern "C" int byol_bn_bwd_reduce(const void* g, const void* x, const void* act,
     bn_bwd_reduce_kernel<0><<<blocks, 256, 2 * C * sizeof(float), stream>>>(gp, xp, ap, scale, shift, mean, invstd, s12, s12 + C, M, C, rows_per_block);
   else if (mask_mode == 1)
     bn_bwd_reduce_kernel<1><<<blocks, 256, 2 * C * sizeof(float), stream>>>(gp, xp, ap, scale, shift, mean, invstd, s12, s12 + C, M, C, rows_per_block);
-  else
+  else if (mask_mode == 2)
     bn_bwd_reduce_kernel<2><<<blocks, 256, 2 * C * sizeof(float), stream>>>(gp, xp, ap, scale, shift, mean, invstd, s12, s12 + C, M, C, rows_per_block);
+  else
+    bn_bwd_reduce_kernel<3><<<blocks, 256, 2 * C * sizeof(float), stream>>>(gp, xp, ap, scale, shift, mean, invstd, s12, s12 + C, M, C, rows_per_block);
   return check_launch("bn_bwd_reduce_kernel");
 }
 
@@ -526,6 +555,7 @@ extern "C" int byol_bn_bwd_apply(const void* g, const void* x, const void* act, 
                                  const float* s12_local, float* dgamma, float* dbeta, cudaStream_t stream) {
   if (s12_local == nullptr) s12_local = s12;
   BYOL_CHECK_ARG(g && x && mean && invstd && gamma && s12 && dy && M > 0 && C % 8 == 0, "byol_bn_bwd_apply: bad args");
+  BYOL_CHECK_ARG(mask_mode >= 0 && mask_mode <= 3 && (mask_mode < 2 || act), "byol_bn_bwd_apply: bad mask_mode %d", mask_mode);
   const int64_t nvec = (int64_t)M * C / 8;
   const float inv_count = (float)(1.0 / count);
   const bf16 *gp = (const bf16*)g, *xp = (const bf16*)x, *ap = (const bf16*)act;
@@ -535,8 +565,10 @@ extern "C" int byol_bn_bwd_apply(const void* g, const void* x, const void* act, 
       bn_bwd_apply_fixed_kernel<0><<<fg, 256, 0, stream>>>(gp, xp, ap, scale, shift, mean, invstd, gamma, s12, s12 + C, inv_count, (bf16*)dy, (bf16*)dz_out, nvec, C, s12_local, s12_local + C, dgamma, dbeta);
     else if (mask_mode == 1)
       bn_bwd_apply_fixed_kernel<1><<<fg, 256, 0, stream>>>(gp, xp, ap, scale, shift, mean, invstd, gamma, s12, s12 + C, inv_count, (bf16*)dy, (bf16*)dz_out, nvec, C, s12_local, s12_local + C, dgamma, dbeta);
-    else
+    else if (mask_mode == 2)
       bn_bwd_apply_fixed_kernel<2><<<fg, 256, 0, stream>>>(gp, xp, ap, scale, shift, mean, invstd, gamma, s12, s12 + C, inv_count, (bf16*)dy, (bf16*)dz_out, nvec, C, s12_local, s12_local + C, dgamma, dbeta);
+    else
+      bn_bwd_apply_fixed_kernel<3><<<fg, 256, 0, stream>>>(gp, xp, ap, scale, shift, mean, invstd, gamma, s12, s12 + C, inv_count, (bf16*)dy, (bf16*)dz_out, nvec, C, s12_local, s12_local + C, dgamma, dbeta);
     return check_launch("bn_bwd_apply_fixed_kernel");
   }
   const int grid = grid_for(nvec, 256);
@@ -544,8 +576,10 @@ extern "C" int byol_bn_bwd_apply(const void* g, const void* x, const void* act, 
     bn_bwd_apply_kernel<0><<<grid, 256, 0, stream>>>(gp, xp, ap, scale, shift, mean, invstd, gamma, s12, s12 + C, inv_count, (bf16*)dy, (bf16*)dz_out, nvec, C, s12_local, s12_local + C, dgamma, dbeta);
   else if (mask_mode == 1)
     bn_bwd_apply_kernel<1><<<grid, 256, 0, stream>>>(gp, xp, ap, scale, shift, mean, invstd, gamma, s12, s12 + C, inv_count, (bf16*)dy, (bf16*)dz_out, nvec, C, s12_local, s12_local + C, dgamma, dbeta);
-  else
+  else if (mask_mode == 2)
     bn_bwd_apply_kernel<2><<<grid, 256, 0, stream>>>(gp, xp, ap, scale, shift, mean, invstd, gamma, s12, s12 + C, inv_count, (bf16*)dy, (bf16*)dz_out, nvec, C, s12_local, s12_local + C, dgamma, dbeta);
+  else
+    bn_bwd_apply_kernel<3><<<grid, 256, 0, stream>>>(gp, xp, ap, scale, shift, mean, invstd, gamma, s12, s12 + C, inv_count, (bf16*)dy, (bf16*)dz_out, nvec, C, s12_local, s12_local + C, dgamma, dbeta);
   return check_launch("bn_bwd_apply_kernel");
 }
 

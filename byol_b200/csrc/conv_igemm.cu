@@ -18,6 +18,7 @@
 // smem operand tiles use the 128-byte swizzle; accumulators live in TMEM.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -33,6 +34,7 @@ struct ConvGemmParams {
   const bf16* src;     // gathered operand, NHWC [Nimg, Hs, Ws, C]
   void* dst;           // output [M, ldc] row-major (bf16 or fp32)
   const bf16* resid;   // optional, [M, ldc] bf16, added in the epilogue
+  const uint8_t* resid_mask;   // optional ReLU mask bits over the same [M, ldc] index space: add resid only where set
   const float* bias;   // optional, [Ndim]
   float* col_sum;      // optional, [Ndim] fp32: += sum over rows of the stored value
   float* col_sqsum;    // optional, [Ndim] fp32: += sum over rows of value^2
@@ -84,36 +86,128 @@ __device__ __forceinline__ TileInfo tile_info(const ConvGemmParams& p, int tile,
   return t;
 }
 
-template <int BN, int STAGES>
+// Epilogue geometry.  The TMA-operand variant (plain GEMM: 1x1 / stride 1 convolutions and the MLP layers) has no
+// gather warps and is bound by its epilogue (few k-blocks per tile, outputs up to 4x the inputs), so it runs EIGHT
+// epilogue warps: warps w and w + 4 share TMEM lane quarter w & 3 and split the tile's columns.
+//   WIDE (BN = 128, 8 warps): each warp stages its [32 rows][64 cols] as 128-byte swizzled rows and issues ONE TMA
+//   store per tile (full 128-byte row segments in global memory); 32 KB of staging, so the operand ring has 2 stages.
+//   narrow: [32 rows][32 cols] chunks with the 64-byte swizzle, NBUF staging buffers per warp.
+template <int BN, int STAGES, bool A_TMA, bool WIDE>
 struct SmemLayout {
+  static constexpr int EW = A_TMA ? 8 : 4;                // epilogue warps
+  static constexpr int CPW = (BN / 32) / (EW / 4);        // 32-column chunks per epilogue warp
+  static constexpr int NBUF = (A_TMA && BN == 128) ? 1 : 2;
+  static constexpr int STAGE_PER_WARP = WIDE ? 4096 : NBUF * 2048;
+  static_assert(!WIDE || CPW == 2, "wide staging = 64 columns per warp");
   static constexpr int B_STAGE_BYTES = BN * 128;
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
-  // output staging: 4 epilogue warps x 2 buffers x [32 rows][64 B].  The TMA 64-byte swizzle pattern repeats every
-  // 512 B, so every buffer must start on a 512-byte boundary (here: 1024-aligned base + multiples of 2048).
+  // output staging.  The TMA swizzle patterns repeat every 512 B (64-byte mode) / 1024 B (128-byte mode), so every
+  // buffer starts on such a boundary (1024-aligned base + multiples of 2048 / 4096).
   static constexpr int STAGE_OUT_OFF = B_OFF + STAGES * B_STAGE_BYTES;
-  static constexpr int BAR_OFF = STAGE_OUT_OFF + 4 * 2 * 2048;
+  static constexpr int BAR_OFF = STAGE_OUT_OFF + EW * STAGE_PER_WARP;
   static constexpr int NEEDED = BAR_OFF + 256;
   static constexpr int TOTAL = NEEDED + 768;   // slack for the run-time 1024-byte alignment of the base
   static_assert(TOTAL <= 115712, "two CTAs per SM need <= 113 KB of dynamic shared memory each");
 };
+
+// packed fp32x2 helpers (FADD2 / FFMA2 on sm_100): the statistics loops do two columns per instruction
+__device__ __forceinline__ uint64_t f2_pack(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 f2_unpack(uint64_t v) {
+  uint32_t lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  return make_float2(__uint_as_float(lo), __uint_as_float(hi));
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t w;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(addr));
+  return w;
+}
+// one staged word = two bf16 columns -> {sum, sum of squares} accumulators
+__device__ __forceinline__ void stat_acc(uint32_t w, uint64_t& s1, uint64_t& s2) {
+  const uint64_t x = f2_pack(w << 16, w & 0xffff0000u);
+  s1 = f2_add(s1, x);
+  s2 = f2_fma(x, x, s2);
+}
+
+// Column statistics of a staged narrow chunk ([32 rows][64 B], 16-byte chunk j of row r at j ^ ((r >> 1) & 3)).
+// lane -> column pair cp = lane & 15 of rows with parity lane >> 4 (two adjacent rows per warp-wide load: all 32
+// banks, no conflicts); the caller combines the two parities with one shuffle when it flushes.
+__device__ __forceinline__ void stats_narrow(uint32_t stage_base, int lane, int rows_valid, uint64_t& s1,
+                                             uint64_t& s2) {
+  const uint32_t cp = (uint32_t)lane & 15u, rh = (uint32_t)lane >> 4;
+  const uint32_t jc = cp >> 2, wq = cp & 3u;
+  uint32_t offq[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) offq[q] = stage_base + rh * 64u + ((jc ^ (uint32_t)q) << 4) + wq * 4u;
+  uint64_t a1 = 0ull, a2 = 0ull, b1 = 0ull, b2 = 0ull;
+  if (rows_valid == 32) {
+#pragma unroll
+    for (int rr = 0; rr < 16; rr += 2) {   // row = 2*rr + rh, so (row >> 1) & 3 == rr & 3
+      stat_acc(lds32(offq[rr & 3] + (uint32_t)rr * 128u), a1, a2);
+      stat_acc(lds32(offq[(rr + 1) & 3] + (uint32_t)(rr + 1) * 128u), b1, b2);
+    }
+  } else {
+    for (int rr = 0; rr < 16; ++rr)
+      if (2 * rr + (int)rh < rows_valid) stat_acc(lds32(offq[rr & 3] + (uint32_t)rr * 128u), a1, a2);
+  }
+  s1 = f2_add(s1, f2_add(a1, b1));
+  s2 = f2_add(s2, f2_add(a2, b2));
+}
+
+// Same for a wide staging tile ([32 rows][128 B], 16-byte chunk c of row r at c ^ (r & 7)): lane -> columns
+// 2*lane, 2*lane + 1 over all 32 rows (one full row per warp-wide load).
+__device__ __forceinline__ void stats_wide(uint32_t stage_base, int lane, int rows_valid, uint64_t& s1, uint64_t& s2) {
+  const uint32_t c = (uint32_t)lane >> 2, wq = (uint32_t)lane & 3u;
+  uint32_t offq[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) offq[q] = stage_base + ((c ^ (uint32_t)q) << 4) + wq * 4u;
+  uint64_t a1 = 0ull, a2 = 0ull, b1 = 0ull, b2 = 0ull;
+  if (rows_valid == 32) {
+#pragma unroll
+    for (int r = 0; r < 32; r += 2) {
+      stat_acc(lds32(offq[r & 7] + (uint32_t)r * 128u), a1, a2);
+      stat_acc(lds32(offq[(r + 1) & 7] + (uint32_t)(r + 1) * 128u), b1, b2);
+    }
+  } else {
+    for (int r = 0; r < rows_valid; ++r) stat_acc(lds32(offq[r & 7] + (uint32_t)r * 128u), a1, a2);
+  }
+  s1 = f2_add(s1, f2_add(a1, b1));
+  s2 = f2_add(s2, f2_add(a2, b2));
+}
 
 // ---------------------------------------------------------------------------------------------
 // fprop / dgrad kernel — persistent: each CTA loops over output tiles (tile = blockIdx.x + i*gridDim.x,
 // n-tile fastest so that concurrently running CTAs share the A tile through L2).  The smem operand ring and
 // the two TMEM accumulator stages run across tile boundaries, so the producers prefetch tile i+1 and the
 // tensor core works on it while the epilogue warps drain tile i.
-//   warps 0-3           : epilogue (TMEM lanes 32*w .. 32*w+31)
-//   warps 4-7 (!A_TMA)  : A-operand gather producers
+//   warps 0 .. EW-1     : epilogue (TMEM lanes 32*(w & 3) .. +31, column group w >> 2)
+//   next 4 (!A_TMA)     : A-operand gather producers
 //   next warp           : MMA issuer (+ TMEM alloc / dealloc)
 //   last warp           : barrier init + TMA producer
 // ---------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool A_TMA>
-__global__ void __launch_bounds__(A_TMA ? 192 : 320, 2)
+template <int BN, int STAGES, bool A_TMA, bool WIDE>
+__global__ void __launch_bounds__(320, 2)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                   const __grid_constant__ CUtensorMap tmapC, const ConvGemmParams p, const int num_tiles) {
-  using L = SmemLayout<BN, STAGES>;
-  constexpr int MMA_WARP = A_TMA ? 4 : 8;
+  using L = SmemLayout<BN, STAGES, A_TMA, WIDE>;
+  constexpr int EW = L::EW;
+  constexpr int CPW = L::CPW;
+  constexpr int MMA_WARP = 8;
   constexpr int TMA_WARP = MMA_WARP + 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -138,7 +232,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1u);
-      mbar_init(&tempty_bar[a], 4u);   // one arrival per epilogue warp
+      mbar_init(&tempty_bar[a], (uint32_t)EW);   // one arrival per epilogue warp
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmapB);
@@ -154,42 +248,61 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < EW) {
     // ======================= epilogue =====================================================
-    // Per 32-column chunk: TMEM -> registers -> (bias / residual / ReLU) -> bf16 -> this warp's swizzled
-    // smem staging tile [32 rows][64 B] -> one TMA store (no LSU global stores).  While the TMA engine reads the
-    // staging tile, the warp sums its 32 rows per column from the same tile (lane = column) for the fused
-    // BatchNorm statistics; the sums stay in registers across all tiles of this CTA that share a column block.
+    // Per 32-column chunk: TMEM -> registers -> (bias / residual / ReLU) -> bf16 -> this warp's swizzled smem
+    // staging -> TMA store (no LSU global stores).  While the TMA engine reads the staging tile, the warp sums its
+    // 32 rows per column from the same tile for the fused BatchNorm statistics (packed fp32x2 arithmetic on two
+    // columns per lane); the sums stay in registers across all tiles of this CTA that share a column block.
     const bool do_stats = p.col_sum != nullptr;
-    // two staging buffers per warp: chunk i+1 is converted and staged while the TMA engine still reads chunk i
-    const uint32_t stage_base0 = smem_u32(stage_out + warp * 4096);
+    const int quarter = warp & 3;                 // TMEM lane quarter = tile rows 32*quarter ..
+    const int col_w0 = (warp >> 2) * (CPW * 32);  // first tile column of this warp
+    const uint32_t stage_base0 = smem_u32(stage_out + warp * L::STAGE_PER_WARP);
     int sbuf = 0;
-    float csum[BN / 32], csq[BN / 32];
+    constexpr int NACC = WIDE ? 1 : CPW;
+    uint64_t cs1[NACC], cs2[NACC];   // packed {even, odd} column sums / sums of squares
 #pragma unroll
-    for (int i = 0; i < BN / 32; ++i) { csum[i] = 0.f; csq[i] = 0.f; }
+    for (int i = 0; i < NACC; ++i) { cs1[i] = 0ull; cs2[i] = 0ull; }
     int local = 0;
     int stat_n0 = -1;   // column offset the register accumulators currently belong to
+    auto flush_stats = [&]() {
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) {
+        float2 a = f2_unpack(cs1[i]), b = f2_unpack(cs2[i]);
+        int col;
+        bool owner = true;
+        if (WIDE) {
+          col = stat_n0 + col_w0 + 2 * lane;
+        } else {
+          // lanes l and l ^ 16 hold the two row parities of the same column pair
+          a.x += __shfl_xor_sync(0xffffffffu, a.x, 16);
+          a.y += __shfl_xor_sync(0xffffffffu, a.y, 16);
+          b.x += __shfl_xor_sync(0xffffffffu, b.x, 16);
+          b.y += __shfl_xor_sync(0xffffffffu, b.y, 16);
+          col = stat_n0 + col_w0 + i * 32 + 2 * (lane & 15);
+          owner = lane < 16;
+        }
+        if (owner && col < p.Ndim) {   // Ndim is a multiple of 8: col + 1 is valid too
+          atomicAdd(p.col_sum + col, a.x);
+          atomicAdd(p.col_sum + col + 1, a.y);
+          atomicAdd(p.col_sqsum + col, b.x);
+          atomicAdd(p.col_sqsum + col + 1, b.y);
+        }
+        cs1[i] = 0ull; cs2[i] = 0ull;
+      }
+    };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const TileInfo ti = tile_info(p, tile, BN);
       const int m0 = ti.m0;
       const int n0 = ti.n0;
       if (do_stats && stat_n0 != n0) {
-        if (stat_n0 >= 0) {
-#pragma unroll
-          for (int i = 0; i < BN / 32; ++i) {
-            if (stat_n0 + i * 32 + lane < p.Ndim) {
-              atomicAdd(p.col_sum + stat_n0 + i * 32 + lane, csum[i]);
-              atomicAdd(p.col_sqsum + stat_n0 + i * 32 + lane, csq[i]);
-            }
-            csum[i] = 0.f; csq[i] = 0.f;
-          }
-        }
+        if (stat_n0 >= 0) flush_stats();
         stat_n0 = n0;
       }
       const int acc = local & 1;
       mbar_wait(&tfull_bar[acc], (uint32_t)((local >> 1) & 1));
       tc_fence_after_sync();
-      const int mrow0 = m0 + warp * 32;
+      const int mrow0 = m0 + quarter * 32;
       int m = mrow0 + lane;
       const bool mvalid = m < p.M;
       if (p.parity) {
@@ -203,13 +316,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       }
       int rows_valid = p.M - mrow0;
       rows_valid = rows_valid < 0 ? 0 : (rows_valid > 32 ? 32 : rows_valid);
+      if (WIDE) {
+        // the single staging tile of this warp: last tile's TMA store has read it, all lanes finished its statistics
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
 #pragma unroll
-      for (int ci = 0; ci < BN / 32; ++ci) {
-        const int c0 = ci * 32;
+      for (int cl = 0; cl < CPW; ++cl) {
+        const int c0 = col_w0 + cl * 32;
         uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), r);
         tmem_ld_wait();
-        if (ci == BN / 32 - 1) {
+        if (cl == CPW - 1) {
           // last TMEM read of this tile: hand the accumulator stage back to the MMA warp
           tc_fence_before_sync();
           __syncwarp();
@@ -227,16 +345,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         }
         if (p.resid != nullptr && mvalid) {
           const bf16* rp = p.resid + (int64_t)m * p.ldc + nbase;
+          const uint8_t* mp = p.resid_mask != nullptr ? p.resid_mask + (((int64_t)m * p.ldc + nbase) >> 3) : nullptr;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             if (nbase + j < p.Ndim) {
               uint4 q = *reinterpret_cast<const uint4*>(rp + j);
+              const uint32_t mb = mp != nullptr ? (uint32_t)__ldg(mp + (j >> 3)) : 0xffu;
               const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float2 f = __bfloat1622float2(h[e]);
-                v[j + 2 * e] += f.x;
-                v[j + 2 * e + 1] += f.y;
+                v[j + 2 * e] += ((mb >> (2 * e)) & 1u) ? f.x : 0.f;
+                v[j + 2 * e + 1] += ((mb >> (2 * e + 1)) & 1u) ? f.y : 0.f;
               }
             }
           }
@@ -269,11 +389,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
               if (nbase + j < p.Ndim)
                 *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
+        } else if (WIDE) {
+          // row = lane, 16-byte chunk c = 4*cl + j at (c ^ (row & 7)) (= the TMA 128-byte swizzle; the 8 lanes of a
+          // store phase hit 8 different 16-byte slots)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 q;
+            q.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+            q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+            q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            const uint32_t off = (uint32_t)lane * 128u + (uint32_t)(((cl * 4 + j) ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_base0 + off), "r"(q.x), "r"(q.y),
+                         "r"(q.z), "r"(q.w)
+                         : "memory");
+          }
         } else {
           // stage this warp's [32 rows][32 cols] bf16 block: row = lane, 16-byte chunk j at (j ^ ((row >> 1) & 3))
           // (= the TMA 64-byte swizzle), which also spreads the 32 row-writes over all banks
           const uint32_t stage_base = stage_base0 + (uint32_t)sbuf * 2048u;
-          if (lane == 0) tma_store_wait_read1();   // the store that used THIS buffer two chunks ago has read it
+          // the store that last used THIS buffer has read it (and every lane is past its statistics loop)
+          if (lane == 0) { if (L::NBUF == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -293,51 +429,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             tma_store_2d(&tmapC, stage_base, nbase, mrow0);   // rows >= M and columns >= Ndim are clipped by TMA
             tma_store_commit();
           }
-          if (do_stats) {
-            // lane = column: sum the stored (bf16-rounded) values of this warp's valid rows.  Fully unrolled:
-            // the swizzle term ((row >> 1) & 3) is a compile-time constant per row, so each row costs
-            // one ld.shared.u16 + shift + FADD + FFMA.
-            const uint32_t jc = (uint32_t)lane >> 3, e2 = ((uint32_t)lane & 7u) * 2u;
-            uint32_t offq[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) offq[q] = stage_base + ((jc ^ (uint32_t)q) << 4) + e2;
-            float s1 = 0.f, s2 = 0.f;
-            if (rows_valid == 32) {
-#pragma unroll
-              for (int rr = 0; rr < 32; ++rr) {
-                uint16_t hv;
-                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(offq[(rr >> 1) & 3] + (uint32_t)rr * 64u));
-                const float x = __uint_as_float((uint32_t)hv << 16);
-                s1 += x;
-                s2 = fmaf(x, x, s2);
-              }
-            } else {
-              for (int rr = 0; rr < rows_valid; ++rr) {
-                uint16_t hv;
-                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(offq[(rr >> 1) & 3] + (uint32_t)rr * 64u));
-                const float x = __uint_as_float((uint32_t)hv << 16);
-                s1 += x;
-                s2 = fmaf(x, x, s2);
-              }
-            }
-            csum[ci] += s1;
-            csq[ci] += s2;
-          }
-          sbuf ^= 1;
+          if (do_stats) stats_narrow(stage_base, lane, rows_valid, cs1[cl], cs2[cl]);
+          if (L::NBUF == 2) sbuf ^= 1;
         }
       }
-    }
-    if (do_stats && stat_n0 >= 0) {
-#pragma unroll
-      for (int i = 0; i < BN / 32; ++i) {
-        if (stat_n0 + i * 32 + lane < p.Ndim) {
-          atomicAdd(p.col_sum + stat_n0 + i * 32 + lane, csum[i]);
-          atomicAdd(p.col_sqsum + stat_n0 + i * 32 + lane, csq[i]);
+      if (WIDE && n0 + col_w0 < p.Ndim) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmapC, stage_base0, n0 + col_w0, mrow0);   // [32 rows][64 cols], clipped at M / Ndim
+          tma_store_commit();
         }
+        if (do_stats) stats_wide(stage_base0, lane, rows_valid, cs1[0], cs2[0]);
       }
     }
+    if (do_stats && stat_n0 >= 0) flush_stats();
     if (lane == 0) tma_store_wait_all();   // global writes complete before the kernel exits
-  } else if (!A_TMA && warp < 8) {
+  } else if (!A_TMA && warp >= EW && warp < EW + 4) {
     // ======================= A gather producers ==========================================
     const int tid = threadIdx.x - 128;
     const int chunk = tid & 7;   // 16-byte chunk inside the 128-byte k-row
@@ -916,11 +1024,11 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int STAGES, bool A_TMA>
+template <int BN, int STAGES, bool A_TMA, bool WIDE>
 static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                         const ConvGemmParams& p, int tiles_m, cudaStream_t stream) {
-  using L = SmemLayout<BN, STAGES>;
-  auto kern = conv_igemm_kernel<BN, STAGES, A_TMA>;
+  using L = SmemLayout<BN, STAGES, A_TMA, WIDE>;
+  auto kern = conv_igemm_kernel<BN, STAGES, A_TMA, WIDE>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
@@ -933,7 +1041,7 @@ static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   const int num_tiles = tiles_m * p.tiles_n;
   int grid = 2 * sm_count();           // persistent: two CTAs per SM (smem and TMEM sized for it)
   if (grid > num_tiles) grid = num_tiles;
-  kern<<<grid, A_TMA ? 192 : 320, L::TOTAL, stream>>>(ta, tb, tc, p, num_tiles);
+  kern<<<grid, 320, L::TOTAL, stream>>>(ta, tb, tc, p, num_tiles);
   return check_launch("conv_igemm_kernel");
 }
 
@@ -945,8 +1053,8 @@ using namespace byol;
 // mode 0 (fprop):  src coord = o*stride - pad + k
 // mode 1 (dgrad):  src coord = (o + pad - k) / stride  (valid only when divisible); here `src` is dY,
 //                  (Hs, Ws) its spatial size and (Ho, Wo) the spatial size of dX.
-extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const void* resid, const float* bias,
-                               float* col_sum, float* col_sqsum, int Nimg, int Hs, int Ws, int C, int Ho, int Wo,
+extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const void* resid,
+                               const void* resid_mask, const float* bias, float* col_sum, float* col_sqsum, int Nimg, int Hs, int Ws, int C, int Ho, int Wo,
                                int Ndim, int KH, int KW, int stride, int pad, int mode, int ldw, int ldc,
                                int out_fp32, int relu, int force_gather, cudaStream_t stream) {
   BYOL_CHECK_ARG(src && wt && dst, "byol_conv_igemm: null pointer");
@@ -959,7 +1067,8 @@ extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const
   BYOL_CHECK_ARG(M64 > 0 && M64 < (1ll << 31), "byol_conv_igemm: M out of range");
   BYOL_CHECK_ARG((int64_t)Nimg * Hs * Ws * C < (1ll << 40), "byol_conv_igemm: src too large");
   // 3x3 / stride 1 / pad 1 (fprop and its dgrad): shared-memory patch reuse instead of a 9x re-gather
-  if (!force_gather && Hs == Ho && Ws == Wo && ldw >= 9 * C &&
+  BYOL_CHECK_ARG(resid_mask == nullptr || (resid != nullptr && ldc % 8 == 0), "byol_conv_igemm: resid_mask without resid");
+  if (!force_gather && resid_mask == nullptr && Hs == Ho && Ws == Wo && ldw >= 9 * C &&
       patch_conv_applicable(Hs, Ws, C, Ndim, KH, KW, stride, pad, out_fp32, bias, (int64_t)Nimg * Hs * Ws * C))
     return patch_conv_launch(src, wt, dst, resid, col_sum, col_sqsum, Nimg, Hs, Ws, C, Ndim, ldw, ldc, mode, relu,
                              sm_count(), stream);
@@ -968,6 +1077,7 @@ extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const
   p.src = (const bf16*)src;
   p.dst = dst;
   p.resid = (const bf16*)resid;
+  p.resid_mask = (const uint8_t*)resid_mask;
   p.bias = bias;
   p.col_sum = col_sum;
   p.col_sqsum = col_sqsum;
@@ -1013,8 +1123,11 @@ extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const
   CUtensorMap ta, tb, tc;
   memset(&ta, 0, sizeof(ta));
   if (make_tmap_2d(&tb, wt, (uint64_t)Ndim, (uint64_t)p.Kg, (uint64_t)ldw, (uint32_t)BN) != 0) return -3;
+  // plain-GEMM tiles with few k-blocks are epilogue-bound: wide (128-byte) output staging, 2-stage operand ring
+  static const int wide_max_kb = [] { const char* e = getenv("BYOL_IGEMM_WIDE_MAX_KB"); return e ? atoi(e) : 0; }();
+  const bool wide = a_tma && BN == 128 && !out_fp32 && p.num_kb <= wide_max_kb;
   if (!out_fp32) {
-    if (make_tmap_2d(&tc, dst, (uint64_t)p.M, (uint64_t)Ndim, (uint64_t)ldc, 32u, 32u) != 0) return -3;
+    if (make_tmap_2d(&tc, dst, (uint64_t)p.M, (uint64_t)Ndim, (uint64_t)ldc, 32u, wide ? 64u : 32u) != 0) return -3;
   } else {
     tc = tb;
   }
@@ -1024,11 +1137,12 @@ extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const
     ta = tb;
   }
   if (BN == 128) {
-    return a_tma ? launch_igemm<128, 3, true>(ta, tb, tc, p, tiles_m, stream)
-                 : launch_igemm<128, 3, false>(ta, tb, tc, p, tiles_m, stream);
+    if (wide) return launch_igemm<128, 2, true, true>(ta, tb, tc, p, tiles_m, stream);
+    return a_tma ? launch_igemm<128, 3, true, false>(ta, tb, tc, p, tiles_m, stream)
+                 : launch_igemm<128, 3, false, false>(ta, tb, tc, p, tiles_m, stream);
   }
-  return a_tma ? launch_igemm<64, 4, true>(ta, tb, tc, p, tiles_m, stream)
-               : launch_igemm<64, 4, false>(ta, tb, tc, p, tiles_m, stream);
+  return a_tma ? launch_igemm<64, 3, true, false>(ta, tb, tc, p, tiles_m, stream)
+               : launch_igemm<64, 4, false, false>(ta, tb, tc, p, tiles_m, stream);
 }
 
 template <int BN, bool B_TMA>

@@ -285,11 +285,12 @@ class Engine(object):
         return ys, coeffs
 
     @staticmethod
-    def _apply(y, c, relu, resid=None, rc=None):
+    def _apply(y, c, relu, resid=None, rc=None, mask=None):
         C = y.shape[-1]
         out = torch.empty_like(y)
         ops.bn_apply(y.view(-1, C), c[0], c[1], relu, resid=None if resid is None else resid.view(-1, C),
-                     rscale=None if rc is None else rc[0], rshift=None if rc is None else rc[1], out=out.view(-1, C))
+                     rscale=None if rc is None else rc[0], rshift=None if rc is None else rc[1], out=out.view(-1, C),
+                     mask_out=mask)
         return out
 
     def _block_fwd(self, b, xs, lanes, train):
@@ -304,15 +305,19 @@ class Engine(object):
         else:
             a2, y3, c3 = None, None, None
             ylast, clast = y2, c2
+        # block output: the backward pass reads the ReLU mask as bits (1/16 of the activation's bytes)
+        masks = [torch.empty(ylast[i].numel() // 8, dtype=torch.uint8, device=ylast[i].device)
+                 if lanes[i][2] is not None else None for i in range(L)]
         if b.down is not None:
             yd, cd = self._conv_bn(b.down, xs, lanes, train)
-            outs = [self._apply(ylast[i], clast[i], True, resid=yd[i], rc=cd[i]) for i in range(L)]
+            outs = [self._apply(ylast[i], clast[i], True, resid=yd[i], rc=cd[i], mask=masks[i]) for i in range(L)]
         else:
             yd, cd = None, None
-            outs = [self._apply(ylast[i], clast[i], True, resid=xs[i]) for i in range(L)]
+            outs = [self._apply(ylast[i], clast[i], True, resid=xs[i], mask=masks[i]) for i in range(L)]
         for i, (_, _, saved) in enumerate(lanes):
             if saved is not None:
                 saved["blocks"].append({
+                    "mask": masks[i],
                     "x": xs[i], "y1": y1[i], "c1": c1[i], "a1": a1[i], "y2": y2[i], "c2": c2[i],
                     "a2": a2[i] if a2 is not None else None, "y3": y3[i] if y3 is not None else None,
                     "c3": c3[i] if c3 is not None else None, "yd": yd[i] if yd is not None else None,
@@ -421,7 +426,7 @@ class Engine(object):
         s12 = self._bpool.take(L * 2 * C)
         for i in range(L):
             ops.bn_bwd_reduce(gs[i].view(-1, C), ys[i].view(-1, C), cs[i], s12[i * 2 * C:(i + 1) * 2 * C], mask_mode,
-                              act=None if acts is None else acts[i].view(-1, C))
+                              act=None if acts is None else (acts[i] if mask_mode == 3 else acts[i].view(-1, C)))
         rows = ys[0].numel() // C
         count, local = rows, None
         if self.sync and self.world() > 1:
@@ -434,7 +439,8 @@ class Engine(object):
             dz = torch.empty_like(ys[i]) if want_dz else None
             dy = torch.empty_like(ys[i])
             ops.bn_bwd_apply(gs[i].view(-1, C), ys[i].view(-1, C), cs[i], gamma, s12[i * 2 * C:(i + 1) * 2 * C], count,
-                             mask_mode, act=None if acts is None else acts[i].view(-1, C), dy=dy.view(-1, C),
+                             mask_mode, act=None if acts is None else (acts[i] if mask_mode == 3 else acts[i].view(-1, C)),
+                             dy=dy.view(-1, C),
                              dz_out=None if dz is None else dz.view(-1, C),
                              s12_local=None if local is None else local[i * 2 * C:(i + 1) * 2 * C],
                              dgamma=self._gview(u.g_off, C), dbeta=self._gview(u.beta_off, C))
@@ -476,13 +482,14 @@ class Engine(object):
             self._side_used = False
             self._side_refs = []
 
-    def _dgrad(self, u, dys, in_shapes, resids=None):
+    def _dgrad(self, u, dys, in_shapes, resids=None, resid_masks=None):
         wd = self.w_online.wd[u.idx]
         outs = []
         for i, dy in enumerate(dys):
             n, h, w, _ = in_shapes[i]
             outs.append(ops.conv_dgrad(dy, wd, h, w, u.k, u.k, u.stride, u.pad,
-                                       resid=None if resids is None else resids[i]))
+                                       resid=None if resids is None else resids[i],
+                                       resid_mask=None if resid_masks is None else resid_masks[i]))
         return outs
 
     def _block_bwd(self, b, S, gs):
@@ -493,11 +500,18 @@ class Engine(object):
         last = b.c3 if b.kind == "bottleneck" else b.c2
         ylast = [s["y3"] if b.kind == "bottleneck" else s["y2"] for s in S]
         clast = [s["c3"] if b.kind == "bottleneck" else s["c2"] for s in S]
-        dyl, dzs = self._bn_bwd(last, gs, ylast, clast, 2, acts=outs, want_dz=b.down is None)
+        masks = [s["mask"] for s in S]
+        # identity blocks whose first conv is 1x1: the masked gradient of the residual branch is never materialised,
+        # the dgrad epilogue of that conv adds gs where the mask bit is set
+        fuse_resid = b.down is None and b.c1.k == 1
+        dyl, dzs = self._bn_bwd(last, gs, ylast, clast, 3, acts=masks, want_dz=b.down is None and not fuse_resid)
+        resid_masks = None
         if b.down is not None:
-            dyd, _ = self._bn_bwd(b.down, gs, [s["yd"] for s in S], [s["cd"] for s in S], 2, acts=outs)
+            dyd, _ = self._bn_bwd(b.down, gs, [s["yd"] for s in S], [s["cd"] for s in S], 3, acts=masks)
             self._wgrad(b.down, xs, dyd)
             resid = self._dgrad(b.down, dyd, xshapes)
+        elif fuse_resid:
+            resid, resid_masks = gs, masks
         else:
             resid = dzs
         if b.kind == "bottleneck":
@@ -510,7 +524,7 @@ class Engine(object):
         g1 = self._dgrad(b.c2, dy2, [tuple(s["a1"].shape) for s in S])
         dy1, _ = self._bn_bwd(b.c1, g1, [s["y1"] for s in S], [s["c1"] for s in S], 1)
         self._wgrad(b.c1, xs, dy1)
-        return self._dgrad(b.c1, dy1, xshapes, resids=resid)
+        return self._dgrad(b.c1, dy1, xshapes, resids=resid, resid_masks=resid_masks)
 
     def _mlp_bwd(self, mlp, S, douts):
         """douts: per lane fp32 or bf16 [b, out] gradient of the MLP output; returns bf16 grads of its input."""

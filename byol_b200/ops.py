@@ -110,20 +110,21 @@ def conv_fprop(x, w_f, kh, kw, stride, pad, bias=None, resid=None, stats=None, r
         out = torch.empty((n, ho, wo, cout), dtype=F32 if out_fp32 else BF16, device=x.device)
     cs = _ptr(stats)
     cq = (stats.data_ptr() + 4 * cout) if stats is not None else 0
-    check(lib.byol_conv_igemm(_ptr(x), _ptr(w_f), _ptr(out), _ptr(resid), _ptr(bias), cs, cq, n, h, w, c, ho, wo,
+    check(lib.byol_conv_igemm(_ptr(x), _ptr(w_f), _ptr(out), _ptr(resid), 0, _ptr(bias), cs, cq, n, h, w, c, ho, wo,
                               cout, kh, kw, stride, pad, 0, ldw, cout, int(out_fp32), int(relu), int(force_gather),
                               _stream()), "byol_conv_igemm(fprop)")
     return out
 
 
-def conv_dgrad(dy, w_d, h, w, kh, kw, stride, pad, resid=None, out=None, force_gather=False):
-    """dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], w);  w_d is the dgrad layout [Cin, taps*Cout]."""
-    _chk(dy, BF16, "dy"); _chk(w_d, BF16, "w_d"); _chk(resid, BF16, "resid")
+def conv_dgrad(dy, w_d, h, w, kh, kw, stride, pad, resid=None, out=None, force_gather=False, resid_mask=None):
+    """dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], w) (+ resid, optionally only where the bits of resid_mask,
+    the uint8 ReLU mask written by bn_apply, are set);  w_d is the dgrad layout [Cin, taps*Cout]."""
+    _chk(dy, BF16, "dy"); _chk(w_d, BF16, "w_d"); _chk(resid, BF16, "resid"); _chk(resid_mask, torch.uint8, "mask")
     n, ho, wo, cout = dy.shape
     cin, ldw = w_d.shape
     if out is None:
         out = torch.empty((n, h, w, cin), dtype=BF16, device=dy.device)
-    check(lib.byol_conv_igemm(_ptr(dy), _ptr(w_d), _ptr(out), _ptr(resid), 0, 0, 0, n, ho, wo, cout, h, w, cin,
+    check(lib.byol_conv_igemm(_ptr(dy), _ptr(w_d), _ptr(out), _ptr(resid), _ptr(resid_mask), 0, 0, 0, n, ho, wo, cout, h, w, cin,
                               kh, kw, stride, pad, 1, ldw, cin, 0, 0, int(force_gather), _stream()),
           "byol_conv_igemm(dgrad)")
     return out
@@ -200,19 +201,21 @@ def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, coeffs):
     return coeffs
 
 
-def bn_apply(x2d, scale, shift, relu, resid=None, rscale=None, rshift=None, out=None, out_f32=None):
-    _chk(x2d, BF16, "x"); _chk(resid, BF16, "resid")
+def bn_apply(x2d, scale, shift, relu, resid=None, rscale=None, rshift=None, out=None, out_f32=None, mask_out=None):
+    """y = act(x*scale + shift (+ resid | resid*rscale + rshift)); mask_out (uint8 [M*C/8]) receives the bits y > 0."""
+    _chk(x2d, BF16, "x"); _chk(resid, BF16, "resid"); _chk(mask_out, torch.uint8, "mask_out")
     m, c = x2d.shape
     if out is None and out_f32 is None:
         out = torch.empty_like(x2d)
     check(lib.byol_bn_apply(_ptr(x2d), _ptr(scale), _ptr(shift), _ptr(resid), _ptr(rscale), _ptr(rshift), _ptr(out),
-                            _ptr(out_f32), m, c, int(relu), _stream()), "byol_bn_apply")
+                            _ptr(out_f32), _ptr(mask_out), m, c, int(relu), _stream()), "byol_bn_apply")
     return out if out is not None else out_f32
 
 
 def bn_bwd_reduce(g, x, coeffs, s12, mask_mode, act=None):
-    """s12 (zeroed fp32 [2C]) += [sum dz, sum dz*xhat];  mask_mode 0 none / 1 relu(x*scale+shift) / 2 act>0."""
-    _chk(g, BF16, "g"); _chk(x, BF16, "x"); _chk(act, BF16, "act")
+    """s12 (zeroed fp32 [2C]) += [sum dz, sum dz*xhat];  mask_mode 0 none / 1 relu(x*scale+shift) / 2 act>0 /
+    3 mask bits (act = the uint8 mask written by bn_apply)."""
+    _chk(g, BF16, "g"); _chk(x, BF16, "x"); _chk(act, torch.uint8 if mask_mode == 3 else BF16, "act")
     m, c = x.shape
     check(lib.byol_bn_bwd_reduce(_ptr(g), _ptr(x), _ptr(act), _ptr(coeffs[0]), _ptr(coeffs[1]), _ptr(coeffs[2]),
                                  _ptr(coeffs[3]), _ptr(s12), m, c, mask_mode, _stream()), "byol_bn_bwd_reduce")
@@ -223,7 +226,7 @@ def bn_bwd_apply(g, x, coeffs, gamma, s12, count, mask_mode, act=None, dy=None, 
                  dgamma=None, dbeta=None):
     """dy = gamma*invstd*(dz - s1/n - xhat*s2/n) with the (global) sums s12 over `count` rows; when dgamma/dbeta
     are given they are incremented by the rank-local sums (s12_local, default s12)."""
-    _chk(g, BF16, "g"); _chk(x, BF16, "x"); _chk(act, BF16, "act")
+    _chk(g, BF16, "g"); _chk(x, BF16, "x"); _chk(act, torch.uint8 if mask_mode == 3 else BF16, "act")
     m, c = x.shape
     if dy is None:
         dy = torch.empty_like(x)

@@ -36,9 +36,11 @@ int byol_device_sm_count(void);
  * sum / sum-of-squares of the stored values (BatchNorm statistics).
  *   mode 0 (fprop): src = x [Nimg,Hs,Ws,C], src coordinate = o*stride - pad + k
  *   mode 1 (dgrad): src = dY [Nimg,Hs,Ws,C=Cout], (Ho,Wo) = spatial size of dX, coordinate = (o + pad - k)/stride
- * wt: bf16 [Ndim, ldw] K-major with k = (kh*KW + kw)*C + c (made by byol_prep_weight). */
-int byol_conv_igemm(const void* src, const void* wt, void* dst, const void* resid, const float* bias,
-                    float* col_sum, float* col_sqsum, int Nimg, int Hs, int Ws, int C, int Ho, int Wo, int Ndim,
+ * wt: bf16 [Ndim, ldw] K-major with k = (kh*KW + kw)*C + c (made by byol_prep_weight).
+ * resid_mask (optional, uint8 [M*ldc/8], written by byol_bn_apply): resid is added only where its bit is set, i.e.
+ * the epilogue applies the ReLU mask of the residual branch (block backward, torchvision resnet.py Bottleneck.forward). */
+int byol_conv_igemm(const void* src, const void* wt, void* dst, const void* resid, const void* resid_mask,
+                    const float* bias, float* col_sum, float* col_sqsum, int Nimg, int Hs, int Ws, int C, int Ho, int Wo, int Ndim,
                     int KH, int KW, int stride, int pad, int mode, int ldw, int ldc, int out_fp32, int relu,
                     int force_gather, byol_stream_t stream);
 
@@ -62,10 +64,13 @@ int byol_bn_finalize_lanes(const float* stats, double count, int L, const float*
                            float momentum, float eps, float* coeffs, int C, byol_stream_t stream);
 int byol_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                         float eps, float* scale, float* shift, int C, byol_stream_t stream);
-/* y = act(x*scale + shift + (resid | resid*rscale + rshift)) */
+/* y = act(x*scale + shift + (resid | resid*rscale + rshift)); mask_out (optional, uint8 [M*C/8]): bit e of byte i =
+ * (y[8*i + e] > 0), the ReLU mask the backward kernels read instead of the activation (mask_mode 3) */
 int byol_bn_apply(const void* x, const float* scale, const float* shift, const void* resid, const float* rscale,
-                  const float* rshift, void* y, float* y_f32, int M, int C, int relu, byol_stream_t stream);
-/* s12 (zeroed [2C]) += [sum dz, sum dz*xhat]; mask_mode 0 none / 1 relu(x*scale+shift) / 2 act > 0 */
+                  const float* rshift, void* y, float* y_f32, void* mask_out, int M, int C, int relu,
+                  byol_stream_t stream);
+/* s12 (zeroed [2C]) += [sum dz, sum dz*xhat]; mask_mode 0 none / 1 relu(x*scale+shift) / 2 act > 0 (act = bf16
+ * activation) / 3 mask bits (act = uint8 mask written by byol_bn_apply) */
 int byol_bn_bwd_reduce(const void* g, const void* x, const void* act, const float* scale, const float* shift,
                        const float* mean, const float* invstd, float* s12, int M, int C, int mask_mode,
                        byol_stream_t stream);

@@ -156,6 +156,25 @@ def test_conv_dgrad_parity_with_residual(cuda):
     assert_close("dgrad_parity_resid", dx, ref, atol=1e-2 * float(ref.abs().max()), rtol=0)
 
 
+@pytest.mark.parametrize("hw,cin,cout", [(14, 256, 64), (9, 64, 128), (8, 512, 2048)])
+def test_conv_dgrad_masked_residual(cuda, hw, cin, cout):
+    """Bottleneck identity block: 1x1 dgrad + (gradient of the residual branch where the ReLU-mask bit is set)."""
+    from byol_b200 import ops
+    n, k, s, p = 3, 1, 1, 0
+    g = torch.Generator().manual_seed(23)
+    wt = R.bf16_round(torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5)
+    dy = R.bf16_round(torch.randn(n, hw, hw, cout, generator=g))
+    resid = R.bf16_round(torch.randn(n, hw, hw, cin, generator=g))
+    keep = torch.rand(n, hw, hw, cin, generator=g) > 0.4
+    bits = ((keep.view(-1, 8).to(torch.int32) * (2 ** torch.arange(8, dtype=torch.int32))).sum(1)).to(torch.uint8)
+    _, w_d = ops.prep_weight(wt.to(cuda), cpad=cin, want_dgrad=True)
+    ref = R.conv_dgrad_ref(dy, wt, (hw, hw), s, p) + resid * keep
+    dx = ops.conv_dgrad(dy.to(cuda, torch.bfloat16), w_d, hw, hw, k, k, s, p, resid=resid.to(cuda, torch.bfloat16),
+                        resid_mask=bits.to(cuda))
+    torch.cuda.synchronize()
+    assert_close("dgrad_masked_resid", dx, ref, atol=1e-2 * float(ref.abs().max()), rtol=0)
+
+
 LINEAR_CASES = [("head1", 64, 2048, 4096), ("head2", 64, 4096, 256), ("cls", 96, 2048, 1000), ("pred1", 200, 256, 4096)]
 
 

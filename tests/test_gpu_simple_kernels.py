@@ -71,7 +71,7 @@ def test_bn_apply_residual(cuda):
     assert_close("bn_apply_resid_affine", y2, torch.relu(x * sc + sh + r * rs + rsh), atol=3e-2, rtol=1e-2)
 
 
-@pytest.mark.parametrize("mask_mode", [0, 1, 2])
+@pytest.mark.parametrize("mask_mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("m,c", [(300, 64), (96, 4096)])
 def test_bn_backward(cuda, mask_mode, m, c):
     from byol_b200 import ops
@@ -95,6 +95,14 @@ def test_bn_backward(cuda, mask_mode, m, c):
     dxref, dgamma, dbeta = R.bn_bwd_ref(dz, x, mean, invstd, gamma)
     s12 = torch.zeros(2 * c, device=cuda)
     actd = act.to(cuda, BF) if act is not None else None
+    if mask_mode == 3:
+        # mask bits as bn_apply writes them: out = relu(1*act + 0) = act, bit = out > 0
+        bits = torch.empty(m * c // 8, dtype=torch.uint8, device=cuda)
+        out = ops.bn_apply(actd, torch.ones(c, device=cuda), torch.zeros(c, device=cuda), relu=True, mask_out=bits)
+        torch.cuda.synchronize()
+        expect = (act.view(-1, 8) > 0).to(torch.int32) * (2 ** torch.arange(8, dtype=torch.int32))
+        assert torch.equal(bits.cpu().to(torch.int32), expect.sum(1)) and torch.equal(out.cpu().float(), act)
+        actd = bits
     ops.bn_bwd_reduce(gy.to(cuda, BF), x.to(cuda, BF), coeffs, s12, mask_mode, act=actd)
     dz_out = torch.empty(m, c, device=cuda, dtype=BF)
     dgam, dbet = torch.ones(c, device=cuda), torch.ones(c, device=cuda)
