@@ -4,6 +4,7 @@
 // /root/reference/main.py:237 (`self.base_network(augmentation)`): MaxPool2d(3, 2, 1), AdaptiveAvgPool2d(1),
 // plus the NCHW fp32 -> NHWC bf16 input conversion and the fp32 master -> bf16 K-major weight layouts the
 // tcgen05 kernels consume.  All are HBM-bound streaming kernels: 16-byte vector accesses, grid-stride loops.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace byol {
@@ -371,7 +372,7 @@ extern "C" int byol_prep_weight_fold(const float* w, void* w_fprop, int Cout, in
 extern "C" int byol_prep_weights_multi(const float* flat, void* pool_f, void* pool_d, const int64_t* desc,
                                        int num_units, cudaStream_t stream) {
   BYOL_CHECK_ARG(flat && pool_f && desc && num_units > 0, "byol_prep_weights_multi: bad args");
-  dim3 grid(32, num_units);
+  dim3 grid(128, num_units);   // blocks beyond a small unit's size exit at once; the largest (8M elements) need them   // blocks beyond a small unit's size exit at once; the largest (8M elements) need them
   prep_weights_multi_kernel<<<grid, 256, 0, stream>>>(flat, (bf16*)pool_f, (bf16*)pool_d, desc);
   return check_launch("prep_weights_multi_kernel");
 }

@@ -595,6 +595,8 @@ class Engine(object):
             gs.append(ops.avgpool_bwd(None if rep_g is None else rep_g[i], du, n, h, w, c))
         for bi in range(len(self.blocks) - 1, -1, -1):
             gs = self._block_bwd(self.blocks[bi], [s["blocks"][bi] for s in saved], gs)
+        # (folding the pool backward into both BatchNorm-backward passes was measured ~2 ms/step SLOWER: the window
+        # search runs twice and costs more than the saved write + two reads of the 112x112 gradient map)
         g0 = []
         for i, s in enumerate(saved):
             n, h, w, c = s["a0_shape"]
