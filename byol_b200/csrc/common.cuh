@@ -250,4 +250,93 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// ----------------------------------------------------------------------------
+// 1-D bulk copy global -> shared (any multiple of 16 bytes), completes on an mbarrier
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tmap, uint32_t src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+               "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+// Shared-memory matrix descriptor without swizzle: core matrix = 8 rows x 16 bytes, rows 16 bytes apart;
+// K-major: LBO = byte step between the two 16-byte K chunks of one K = 16 MMA, SBO = step between 8-row groups.
+// (Measured, tools/experiments/noswz_test.cu: LBO / SBO may be smaller than the 128-byte core matrix, i.e. rows and
+// chunks may overlap: the descriptor alone forms the im2col of a 1-D window over 16-byte pixels.)
+__device__ __forceinline__ uint64_t make_smem_desc_none(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// ----------------------------------------------------------------------------
+// epilogue statistics (shared by the igemm and stem kernels)
+// ----------------------------------------------------------------------------
+// packed fp32x2 helpers (FADD2 / FFMA2 on sm_100): the statistics loops do two columns per instruction
+__device__ __forceinline__ uint64_t f2_pack(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 f2_unpack(uint64_t v) {
+  uint32_t lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  return make_float2(__uint_as_float(lo), __uint_as_float(hi));
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t w;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(addr));
+  return w;
+}
+// one staged word = two bf16 columns -> {sum, sum of squares} accumulators
+__device__ __forceinline__ void stat_acc(uint32_t w, uint64_t& s1, uint64_t& s2) {
+  const uint64_t x = f2_pack(w << 16, w & 0xffff0000u);
+  s1 = f2_add(s1, x);
+  s2 = f2_fma(x, x, s2);
+}
+
+// Column statistics of a staged narrow chunk ([32 rows][64 B], 16-byte chunk j of row r at j ^ ((r >> 1) & 3)).
+// lane -> column pair cp = lane & 15 of rows with parity lane >> 4 (two adjacent rows per warp-wide load: all 32
+// banks, no conflicts); the caller combines the two parities with one shuffle when it flushes.
+__device__ __forceinline__ void stats_narrow(uint32_t stage_base, int lane, int rows_valid, uint64_t& s1,
+                                             uint64_t& s2) {
+  const uint32_t cp = (uint32_t)lane & 15u, rh = (uint32_t)lane >> 4;
+  const uint32_t jc = cp >> 2, wq = cp & 3u;
+  uint32_t offq[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) offq[q] = stage_base + rh * 64u + ((jc ^ (uint32_t)q) << 4) + wq * 4u;
+  uint64_t a1 = 0ull, a2 = 0ull, b1 = 0ull, b2 = 0ull;
+  if (rows_valid == 32) {
+#pragma unroll
+    for (int rr = 0; rr < 16; rr += 2) {   // row = 2*rr + rh, so (row >> 1) & 3 == rr & 3
+      stat_acc(lds32(offq[rr & 3] + (uint32_t)rr * 128u), a1, a2);
+      stat_acc(lds32(offq[(rr + 1) & 3] + (uint32_t)(rr + 1) * 128u), b1, b2);
+    }
+  } else {
+    for (int rr = 0; rr < 16; ++rr)
+      if (2 * rr + (int)rh < rows_valid) stat_acc(lds32(offq[rr & 3] + (uint32_t)rr * 128u), a1, a2);
+  }
+  s1 = f2_add(s1, f2_add(a1, b1));
+  s2 = f2_add(s2, f2_add(a2, b2));
+}
+
+
 }  // namespace byol

@@ -52,6 +52,41 @@ def nchw_to_nhwc8(x, out=None):
     return out
 
 
+def stem4_supported(cin, cout, h, w, k, stride, pad):
+    """True if the dedicated stem kernels (7x7/s2/p3, <= 4 -> 64 channels, W <= 256) handle this geometry."""
+    return bool(lib.byol_stem4_supported(cin, cout, h, w, k, stride, pad))
+
+
+def nchw_to_stem4(x):
+    """fp32 NCHW [N, C<=4, H, W] -> zero-padded bf16 NHWC4 [N, H+6, Wp, 4] (input format of the stem kernels)."""
+    _chk(x, F32, "x")
+    n, c, h, w = x.shape
+    out = torch.empty((n, h + 6, lib.byol_stem4_row_pixels(), 4), dtype=BF16, device=x.device)
+    check(lib.byol_nchw_to_stem4(_ptr(x), _ptr(out), n, c, h, w, _stream()), "byol_nchw_to_stem4")
+    return out
+
+
+def prep_weight_stem4(w, out=None):
+    """fp32 [64, Cin, 7, 7] -> bf16 [7, 4, 64, 8] (stem kernel layout)."""
+    _chk(w, F32, "w")
+    if out is None:
+        out = torch.empty(7 * 4 * 64 * 8, dtype=BF16, device=w.device)
+    check(lib.byol_prep_weight_stem4(_ptr(w), _ptr(out), w.shape[1], _stream()), "byol_prep_weight_stem4")
+    return out
+
+
+def stem_conv_fprop(xs4, w_stem4, h, w, stats=None):
+    """y[N, H/2, W/2, 64] = conv7x7/s2/p3 over the padded NHWC4 image; stats (fp32 [128], zeroed): += sum | sum sq."""
+    _chk(xs4, BF16, "xs4"); _chk(w_stem4, BF16, "w_stem4")
+    n = xs4.shape[0]
+    y = torch.empty((n, h // 2, w // 2, 64), dtype=BF16, device=xs4.device)
+    cs = _ptr(stats) if stats is not None else 0
+    cq = _ptr(stats[64:]) if stats is not None else 0
+    check(lib.byol_stem_conv_fprop(_ptr(xs4), _ptr(w_stem4), _ptr(y), cs, cq, n, h, w, _stream()),
+          "byol_stem_conv_fprop")
+    return y
+
+
 def prep_weight(w, cpad=None, want_dgrad=True, out_f=None, out_d=None):
     """fp32 [Cout, Cin, KH, KW] (or [out, in] for Linear) -> (w_fprop bf16 [Cout, taps*Cpad], w_dgrad bf16 [Cin, taps*Cout])."""
     _chk(w, F32, "w")

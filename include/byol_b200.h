@@ -50,6 +50,18 @@ int byol_conv_wgrad(const void* src, const void* dy, float* dw, int Nimg, int Hs
                     int Ho, int Wo, int Cout, int KH, int KW, int stride, int pad, int force_gather,
                     byol_stream_t stream);
 
+/* ---- stem (7x7 / stride 2 / pad 3, <= 4 input channels, 64 output channels, W <= 256): the torchvision ResNet
+ *      conv1 reached from main.py:237.  The image is converted once to zero-padded NHWC4 bf16
+ *      ([N][H+6][264][4]); the kernel forms the im2col rows with overlapping no-swizzle UMMA descriptors. ---- */
+int byol_stem4_supported(int Cin, int Cout, int H, int W, int k, int stride, int pad);
+int byol_stem4_row_pixels(void); /* Wp of the padded image tensor [N][H+6][Wp][4] */
+int byol_nchw_to_stem4(const float* x, void* xs, int N, int Cin, int H, int W, byol_stream_t stream);
+/* w fp32 [64][Cin][7][7] -> ws bf16 [7][4][64][8] (14336 elements) */
+int byol_prep_weight_stem4(const float* w, void* ws, int Cin, byol_stream_t stream);
+/* y [N, H/2, W/2, 64] bf16; col_sum / col_sqsum (both or none): += per-channel sum / sum of squares of y */
+int byol_stem_conv_fprop(const void* xs, const void* ws, void* y, float* col_sum, float* col_sqsum, int N, int H, int W,
+                         byol_stream_t stream);
+
 /* ---- BatchNorm (train / eval, optionally cross-rank): replaces ATen batch_norm and SyncBatchNorm
  *      (main.py:196,202,237,433; torch/nn/modules/_functions.py:10-205) ---- */
 int byol_bn_stats(const void* x, float* stats /* zeroed [2C] */, int M, int C, byol_stream_t stream);

@@ -140,6 +140,34 @@ def test_stem_folded_layout(cuda, shape):
     assert_close("stem_fold_stats", stats[:64], yr.sum(0), atol=1e-3 * yr.abs().sum(0).max().item(), rtol=0)
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 32), (3, 30, 26), (2, 224, 224), (5, 64, 64), (1, 256, 256)])
+def test_stem4_fprop(cuda, shape):
+    """Dedicated stem kernel: padded NHWC4 input, im2col formed by overlapping no-swizzle UMMA descriptors."""
+    from byol_b200 import ops
+    n, h, w = shape
+    assert ops.stem4_supported(3, 64, h, w, 7, 2, 3)
+    g = torch.Generator().manual_seed(29)
+    x = R.bf16_round(torch.rand(n, 3, h, w, generator=g) - 0.3)        # NCHW fp32 (values exactly bf16)
+    wt = R.bf16_round(torch.randn(64, 3, 7, 7, generator=g) / 12.0)
+    xs4 = ops.nchw_to_stem4(x.to(cuda))
+    ws = ops.prep_weight_stem4(wt.to(cuda))
+    ref = R.conv_fprop_ref(x.permute(0, 2, 3, 1).contiguous(), wt, 2, 3)
+    stats = torch.zeros(128, device=cuda)
+    y = ops.stem_conv_fprop(xs4, ws, h, w, stats=stats)
+    y2 = ops.stem_conv_fprop(xs4, ws, h, w)
+    torch.cuda.synchronize()
+    assert y.shape == (n, h // 2, w // 2, 64) and torch.equal(y, y2)
+    assert_close("stem4", y, ref, atol=1e-2 * float(ref.abs().max()), rtol=0)
+    yr = y.float().cpu().reshape(-1, 64)
+    assert_close("stem4_sum", stats[:64], yr.sum(0), atol=1e-3 * yr.abs().sum(0).max().item(), rtol=0)
+    assert_close("stem4_sqsum", stats[64:], (yr * yr).sum(0), atol=1e-3 * (yr * yr).sum(0).max().item(), rtol=0)
+    # same weights through the generic implicit-GEMM path (NHWC8 input, folded layout): both round the same products
+    x8 = ops.nchw_to_nhwc8(x.to(cuda))
+    y_ig = ops.conv_fprop(x8, ops.prep_weight_fold(wt.to(cuda)), 7, 7, 2, 3)
+    torch.cuda.synchronize()
+    assert_close("stem4_vs_igemm", y, y_ig.float().cpu(), atol=2e-2 * float(ref.abs().max()), rtol=0)
+
+
 def test_conv_dgrad_parity_with_residual(cuda):
     """BasicBlock-style strided 3x3 dgrad with the residual gradient added in the epilogue (parity mode)."""
     from byol_b200 import ops
