@@ -29,6 +29,7 @@ _SIGNATURES = {
     "byol_nchw_to_stem4": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "byol_prep_weight_stem4": [c_void_p, c_void_p, c_int, c_void_p],
     "byol_stem_conv_fprop": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "byol_stem_conv_wgrad": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "byol_conv_wgrad": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                         c_int, c_int, c_int, c_int, c_int, c_void_p],
     "byol_bn_stats": [c_void_p, c_void_p, c_int, c_int, c_void_p],

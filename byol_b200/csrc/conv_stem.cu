@@ -15,6 +15,7 @@
 //   warp 9    : producer (1-D bulk copies of input row pairs into an 8-slot ring; weights once)
 // Replaces the cuDNN stem convolution reached from /root/reference/main.py:237 (torchvision resnet conv1) and its
 // weight gradient under main.py:617.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -220,6 +221,186 @@ stem_fprop_kernel(const __grid_constant__ CUtensorMap tmapY, const StemParams p)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stem weight gradient: dW[co][c][kh][kw] += sum over pixels dY[n, oh, ow, co] * x[n, 2oh + kh - 3, 2ow + kw - 3, c].
+// One work unit = one padded input row v of one image.  Row v meets the output rows oh = (v >> 1) - j with kernel row
+// kh = (v & 1) + 2j (j = 0..3), so per unit two M = 128 MMA chains run over K = the pixels of the row:
+//   A (M-major, 128-byte swizzle) = two ADJACENT dY row tiles [128 px][64 co] (LBO = tile size): rows (a-1, a) and
+//     (a-3, a-2) with a = v >> 1; rows outside the image are TMA out-of-bounds zero tiles
+//   B (N-major, no swizzle)       = the input row itself: N = 8 window pixels x 4 channels, pixel k's window starts
+//     16 bytes after pixel k-1's (overlapping no-swizzle core matrices, as in the forward kernel)
+//   D = four TMEM accumulators [128 = 2 kh x 64 co][32 = (kw, c)] (row parity x chain), kept for the CTA's whole
+//     contiguous range of units and added to the fp32 gradient with atomics at the end.
+// The dY ring has 11 slots + a mirror of slot 0 behind slot 10, so that "row oh-1, row oh" are always adjacent in smem.
+//   warps 0-3: final epilogue, warp 4: MMA issuer, warp 5: producer.
+// ---------------------------------------------------------------------------------------------
+static constexpr int SW_NS = 11;   // 4 rows in use + 7 rows of prefetch (dY streams from HBM: the ring depth hides its latency)
+static constexpr int SW_TILE = 128 * 128;
+static constexpr int SW_NX = 12;
+static constexpr int SW_X_OFF = (SW_NS + 1) * SW_TILE;
+static constexpr int SW_BAR_OFF = SW_X_OFF + SW_NX * ST_ROW_BYTES;
+static constexpr int SW_NEEDED = SW_BAR_OFF + 256;
+static constexpr int SW_TOTAL = SW_NEEDED + 1024;
+static_assert(SW_BAR_OFF % 8 == 0 && SW_TOTAL <= 232448 - 1024, "stem wgrad smem");
+
+struct StemWgradParams {
+  const bf16* xs;   // [N][Hp][264][4]
+  float* dw;        // [64][Cin][7][7] fp32, accumulated
+  int N, Ho, Wo, Hp, Cin;
+  int num_units;    // N * Hp
+  int ksteps;       // ceil(Wo / 16)
+  uint32_t b_lbo, b_sbo;
+};
+
+__device__ __forceinline__ void tma_load_4d_stem(uint32_t dst_smem, const CUtensorMap* tmap, uint64_t* bar, int c0,
+                                                 int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst_smem), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1)
+stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmapDY, const StemWgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  if (smem + SW_NEEDED > smem_raw + SW_TOTAL) __trap();
+  uint8_t* sDY = smem;
+  uint8_t* sX = smem + SW_X_OFF;
+  uint64_t* dfull = (uint64_t*)(smem + SW_BAR_OFF);
+  uint64_t* dempty = dfull + SW_NS;
+  uint64_t* xfull = dempty + SW_NS;
+  uint64_t* xempty = xfull + SW_NX;
+  uint64_t* done = xempty + SW_NX;
+  uint32_t* tmem_slot = (uint32_t*)(done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int u_begin = (int)((int64_t)blockIdx.x * p.num_units / gridDim.x);
+  const int u_end = (int)((int64_t)(blockIdx.x + 1) * p.num_units / gridDim.x);
+
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < SW_NS; ++s) { mbar_init(&dfull[s], 1u); mbar_init(&dempty[s], 1u); }
+    for (int s = 0; s < SW_NX; ++s) { mbar_init(&xfull[s], 1u); mbar_init(&xempty[s], 1u); }
+    mbar_init(done, 1u);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmapDY);
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5) {
+    // ======================= producer =====================================================
+    if (lane == 0) {
+      int q = 0, xq = 0;
+      for (int u = u_begin; u < u_end; ++u) {
+        const int n = u / p.Hp, v = u % p.Hp, a = v >> 1;
+        const bool first = (u == u_begin) || (v == 0);
+        const int r0 = first ? a - 3 : a;
+        const int cnt = first ? 4 : ((v & 1) ? 0 : 1);
+        for (int j = 0; j < cnt; ++j, ++q) {
+          const int slot = q % SW_NS;
+          mbar_wait(&dempty[slot], (uint32_t)(((q / SW_NS) & 1) ^ 1));
+          mbar_arrive_expect_tx(&dfull[slot], (uint32_t)(slot == 0 ? 2 * SW_TILE : SW_TILE));
+          tma_load_4d_stem(smem_u32(sDY + slot * SW_TILE), &tmapDY, &dfull[slot], 0, 0, r0 + j, n);
+          if (slot == 0) tma_load_4d_stem(smem_u32(sDY + SW_NS * SW_TILE), &tmapDY, &dfull[slot], 0, 0, r0 + j, n);
+        }
+        const int xs = xq % SW_NX;
+        mbar_wait(&xempty[xs], (uint32_t)(((xq / SW_NX) & 1) ^ 1));
+        mbar_arrive_expect_tx(&xfull[xs], (uint32_t)ST_ROW_BYTES);
+        bulk_load_1d(smem_u32(sX + xs * ST_ROW_BYTES), p.xs + (int64_t)u * (ST_ROW_BYTES / 2), (uint32_t)ST_ROW_BYTES,
+                     &xfull[xs]);
+        ++xq;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 4) {
+    // ======================= MMA issuer ===================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(1u, 128, 32, 1u, 1u);   // both operands MN-major
+      const uint32_t dy_addr = smem_u32(sDY), x_addr = smem_u32(sX);
+      int qb = 0, qn = 0, xq = 0;
+      uint32_t used = 0;
+      for (int u = u_begin; u < u_end; ++u, ++xq) {
+        const int v = u % p.Hp;
+        const bool first = (u == u_begin) || (v == 0);
+        if (first) {
+          qb = qn;
+          qn += 4;
+          for (int j = 0; j < 4; ++j) mbar_wait(&dfull[(qb + j) % SW_NS], (uint32_t)(((qb + j) / SW_NS) & 1));
+        } else if ((v & 1) == 0) {
+          qb += 1;
+          qn += 1;
+          mbar_wait(&dfull[(qb + 3) % SW_NS], (uint32_t)(((qb + 3) / SW_NS) & 1));
+        }
+        const int xs = xq % SW_NX;
+        mbar_wait(&xfull[xs], (uint32_t)((xq / SW_NX) & 1));
+        tc_fence_after_sync();
+        const uint32_t xrow = x_addr + (uint32_t)(xs * ST_ROW_BYTES);
+#pragma unroll
+        for (int chain = 0; chain < 2; ++chain) {
+          // chain 0: dY rows (a-1, a) <-> kh = (par+2, par); chain 1: rows (a-3, a-2) <-> kh = (par+6, par+4)
+          const int acc = (v & 1) * 2 + chain;
+          const uint32_t tile0 = dy_addr + (uint32_t)(((qb + (chain == 0 ? 2 : 0)) % SW_NS) * SW_TILE);
+          for (int ks = 0; ks < p.ksteps; ++ks) {
+            const uint64_t adesc = make_smem_desc_sw128(tile0 + (uint32_t)(ks * 2048), (uint32_t)SW_TILE, 1024u);
+            const uint64_t bdesc = make_smem_desc_none(xrow + (uint32_t)(ks * 256), p.b_lbo, p.b_sbo);
+            umma_bf16(tmem_base + (uint32_t)(acc * 32), adesc, bdesc, idesc,
+                      (uint32_t)((((used >> acc) & 1u) != 0u) || ks != 0));
+          }
+          used |= 1u << acc;
+        }
+        umma_commit(&xempty[xs]);
+        const bool last = (u + 1 == u_end) || (v == p.Hp - 1);
+        if (last) {
+          for (int j = 0; j < 4; ++j) umma_commit(&dempty[(qb + j) % SW_NS]);
+        } else if (v & 1) {
+          umma_commit(&dempty[qb % SW_NS]);
+        }
+      }
+      umma_commit(done);
+    }
+    __syncwarp();
+  } else {
+    // ======================= epilogue (once) ==============================================
+    if (u_end > u_begin) {
+      mbar_wait(done, 0u);
+      tc_fence_after_sync();
+      const int L = warp * 32 + lane;
+      const int half = L >> 6, co = L & 63;
+      const bool both = (u_end - u_begin) >= 2;
+      const int only_par = (u_begin % p.Hp) & 1;
+      for (int acc = 0; acc < 4; ++acc) {
+        const int par = acc >> 1, chain = acc & 1;
+        if (!both && par != only_par) continue;   // this row parity never ran: the accumulator is uninitialised
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 32), r);
+        tmem_ld_wait();
+        const int kh = par + (chain == 0 ? (half == 0 ? 2 : 0) : (half == 0 ? 6 : 4));
+        if (kh > 6) continue;
+#pragma unroll
+        for (int col = 0; col < 32; ++col) {
+          const int kw = col >> 2, c = col & 3;
+          if (kw < 7 && c < p.Cin) atomicAdd(p.dw + ((co * p.Cin + c) * 7 + kh) * 7 + kw, __uint_as_float(r[col]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
 // fp32 NCHW image -> bf16 [N][H+6][264][4] with the conv padding (3 pixels / rows of zeros) and channel 3 = 0
 __global__ void nchw_to_stem4_kernel(const float* __restrict__ x, bf16* __restrict__ y, int N, int Cin, int H, int W) {
   const int Hp = H + 6;
@@ -345,4 +526,44 @@ extern "C" int byol_stem_conv_fprop(const void* xs, const void* ws, void* y, flo
   if (grid > p.num_tiles) grid = p.num_tiles;
   stem_fprop_kernel<<<grid, 320, ST_TOTAL, stream>>>(tmY, p);
   return check_launch("stem_fprop_kernel");
+}
+
+// dw[64][Cin][7][7] (fp32) += dY^T * im2col(xs); dy: [N, H/2, W/2, 64] bf16
+extern "C" int byol_stem_conv_wgrad(const void* xs, const void* dy, float* dw, int N, int Cin, int H, int W,
+                                    cudaStream_t stream) {
+  BYOL_CHECK_ARG(xs && dy && dw && N > 0 && byol_stem4_supported(Cin, 64, H, W, 7, 2, 3), "byol_stem_conv_wgrad: bad args");
+  const int Ho = H / 2, Wo = W / 2, Hp = H + 6;
+  BYOL_CHECK_ARG((int64_t)N * Hp < (1ll << 31), "byol_stem_conv_wgrad: too many rows");
+  StemWgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.xs = (const bf16*)xs;
+  p.dw = dw;
+  p.N = N; p.Ho = Ho; p.Wo = Wo; p.Hp = Hp; p.Cin = Cin;
+  p.num_units = N * Hp;
+  p.ksteps = (Wo + 15) / 16;
+  // no-swizzle MN-major B: LBO = step between 8-pixel (K) groups, SBO = step between 16-byte N chunks
+  static const int variant = [] { const char* e = getenv("BYOL_STEM_WGRAD_VARIANT"); return e ? atoi(e) : 0; }();
+  p.b_lbo = variant == 0 ? 128u : 16u;
+  p.b_sbo = variant == 0 ? 16u : 128u;
+  PFN_encodeTiledStem fn = stem_encode_fn();
+  if (fn == nullptr) { set_last_error("byol_stem_conv_wgrad: cuTensorMapEncodeTiled unavailable"); return -3; }
+  CUtensorMap tmDY;
+  cuuint64_t dims[4] = {64, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
+  cuuint64_t strides[3] = {128, (cuuint64_t)Wo * 128, (cuuint64_t)Ho * Wo * 128};
+  cuuint32_t box[4] = {64, 128, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(&tmDY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("byol_stem_conv_wgrad: tensor map encode failed (%d)", (int)r); return -3; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_TOTAL);
+    if (e != cudaSuccess) { set_last_error("cudaFuncSetAttribute(stem_wgrad) failed: %s", cudaGetErrorString(e)); return -2; }
+    attr_set = true;
+  }
+  int grid = stem_sm_count();
+  if (grid > p.num_units) grid = p.num_units;
+  stem_wgrad_kernel<<<grid, 192, SW_TOTAL, stream>>>(tmDY, p);
+  return check_launch("stem_wgrad_kernel");
 }

@@ -77,6 +77,11 @@ class _Weights(object):
             rows_d.append(base)
         self.desc_with_dgrad = torch.tensor(rows_d, dtype=torch.int64, device=device)
         self.desc_fprop_only = torch.tensor(rows_n, dtype=torch.int64, device=device)
+        # dedicated stem kernel layout ([7][4][64][8]) when the first conv is the torchvision 7x7/2 stem
+        st = units[0]
+        self.stem4_ok = (st.kind == "conv" and st.k == 7 and st.stride == 2 and st.pad == 3 and st.cin <= 4 and
+                         st.cout == 64)
+        self.w_stem4 = torch.empty(7 * 4 * 64 * 8, dtype=BF16, device=device) if self.stem4_ok else None
 
 
 class _Pool(object):
@@ -243,11 +248,15 @@ class Engine(object):
         """fp32 master (flat vector) -> bf16 tensor-core layouts of every conv / linear, one launch."""
         desc = wset.desc_with_dgrad if (want_dgrad and wset.pool_d is not None) else wset.desc_fprop_only
         ops.prep_weights_multi(flat, wset.pool_f, wset.pool_d, desc)
+        if wset.stem4_ok:
+            st = self.stem
+            ops.prep_weight_stem4(flat[st.w_off:st.w_off + st.w_numel].view(st.cout, st.cin, st.k, st.k),
+                                  out=wset.w_stem4)
 
     # ------------------------------------------------------------------------------------------
     # forward building blocks (lists are per lane)
     # ------------------------------------------------------------------------------------------
-    def _conv_bn(self, u, xs, lanes, train):
+    def _conv_bn(self, u, xs, lanes, train, stem4=None):
         """raw conv/linear outputs + BN coefficients [scale, shift, mean, invstd] per lane."""
         L, C = len(lanes), u.cout
         stats = self._zpool.take(L * 2 * C) if train else None
@@ -256,7 +265,9 @@ class Engine(object):
             st = stats[i * 2 * C:(i + 1) * 2 * C] if train else None
             bias = flat[u.b_off:u.b_off + C] if u.b_off >= 0 else None
             x = xs[i]
-            if u.kind == "linear":
+            if stem4 is not None:
+                y = ops.stem_conv_fprop(stem4[0][i], wset.w_stem4, stem4[1][i][0], stem4[1][i][1], stats=st)
+            elif u.kind == "linear":
                 y = ops.linear_fprop(x, wset.wf[u.idx], bias=bias, stats=st)
             else:
                 y = ops.conv_fprop(x, wset.wf[u.idx], u.k, u.k, u.stride, u.pad, stats=st)
@@ -350,9 +361,14 @@ class Engine(object):
         main = torch.cuda.current_stream()
         conv = {}
         x8 = []
+        st = self.stem
         for a in augs:     # online and target lanes of one view share the converted input
             if id(a) not in conv:
-                conv[id(a)] = ops.nchw_to_nhwc8(a)
+                # padded NHWC4 for the dedicated stem kernels, NHWC8 for the generic path (e.g. 384x384 images)
+                use4 = lanes[0][1].stem4_ok and ops.stem4_supported(st.cin, st.cout, a.shape[2], a.shape[3], st.k,
+                                                                    st.stride, st.pad)
+                conv[id(a)] = (None, ops.nchw_to_stem4(a), a.shape[2], a.shape[3]) if use4 else \
+                    (ops.nchw_to_nhwc8(a), None, a.shape[2], a.shape[3])
             x8.append(conv[id(a)])
         if rep_bf16_out is None:
             rep_bf16_out = [None] * L
@@ -390,7 +406,10 @@ class Engine(object):
         st = self.stem
         self._zpool = _Pool(L * 2 * self.bn_channels, self.device, zero=True) if train else None
         self._cpool = _Pool(L * 4 * self.bn_channels, self.device, zero=False)
-        y0, c0 = self._conv_bn(st, x8, lanes, train)
+        xs4 = [x[1] for x in x8]
+        hw = [(x[2], x[3]) for x in x8]
+        x8 = [x[0] for x in x8]
+        y0, c0 = self._conv_bn(st, x8, lanes, train, stem4=(xs4, hw) if xs4[0] is not None else None)
         xs = []
         for i, (_, _, saved) in enumerate(lanes):
             # stem: BN-apply + ReLU + max-pool fused (the normalised 112x112 map is never written)
@@ -398,7 +417,8 @@ class Engine(object):
                                              want_idx=saved is not None)
             xs.append(p)
             if saved is not None:
-                saved.update({"x8": x8[i], "y0": y0[i], "c0": c0[i], "a0_shape": tuple(y0[i].shape), "pool_idx": idx,
+                saved.update({"x8": x8[i] if xs4[i] is None else (xs4[i], hw[i][0], hw[i][1]),
+                              "y0": y0[i], "c0": c0[i], "a0_shape": tuple(y0[i].shape), "pool_idx": idx,
                               "blocks": []})
         for b in self.blocks:
             xs = self._block_fwd(b, xs, lanes, train)
@@ -469,7 +489,9 @@ class Engine(object):
 
     def _launch_wgrad(self, u, xs, dys, dw):
         for x, dy in zip(xs, dys):
-            if u.kind == "linear":
+            if isinstance(x, tuple):      # stem: (padded NHWC4 image, H, W) -> dedicated kernel
+                ops.stem_conv_wgrad(x[0], dy, dw, x[1], x[2])
+            elif u.kind == "linear":
                 ops.conv_wgrad(x.view(x.shape[0], 1, 1, -1), dy.view(dy.shape[0], 1, 1, -1), dw, 1, 1, 1, 0)
             else:
                 ops.conv_wgrad(x, dy, dw, u.k, u.k, u.stride, u.pad)

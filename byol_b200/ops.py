@@ -87,6 +87,14 @@ def stem_conv_fprop(xs4, w_stem4, h, w, stats=None):
     return y
 
 
+def stem_conv_wgrad(xs4, dy, dw, h, w):
+    """dw[64, Cin, 7, 7] (fp32) += dy^T * im2col(image) for the 7x7/s2/p3 stem; xs4 from nchw_to_stem4."""
+    _chk(xs4, BF16, "xs4"); _chk(dy, BF16, "dy"); _chk(dw, F32, "dw")
+    check(lib.byol_stem_conv_wgrad(_ptr(xs4), _ptr(dy), _ptr(dw), xs4.shape[0], dw.shape[1], h, w, _stream()),
+          "byol_stem_conv_wgrad")
+    return dw
+
+
 def prep_weight(w, cpad=None, want_dgrad=True, out_f=None, out_d=None):
     """fp32 [Cout, Cin, KH, KW] (or [out, in] for Linear) -> (w_fprop bf16 [Cout, taps*Cpad], w_dgrad bf16 [Cin, taps*Cout])."""
     _chk(w, F32, "w")

@@ -62,6 +62,9 @@ int byol_prep_weight_stem4(const float* w, void* ws, int Cin, byol_stream_t stre
 int byol_stem_conv_fprop(const void* xs, const void* ws, void* y, float* col_sum, float* col_sqsum, int N, int H, int W,
                          byol_stream_t stream);
 
+/* dw [64][Cin][7][7] fp32 += dY^T x im2col(xs); dy [N, H/2, W/2, 64] bf16 (autograd of main.py:617 for the stem) */
+int byol_stem_conv_wgrad(const void* xs, const void* dy, float* dw, int N, int Cin, int H, int W, byol_stream_t stream);
+
 /* ---- BatchNorm (train / eval, optionally cross-rank): replaces ATen batch_norm and SyncBatchNorm
  *      (main.py:196,202,237,433; torch/nn/modules/_functions.py:10-205) ---- */
 int byol_bn_stats(const void* x, float* stats /* zeroed [2C] */, int M, int C, byol_stream_t stream);

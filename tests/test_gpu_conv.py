@@ -168,6 +168,25 @@ def test_stem4_fprop(cuda, shape):
     assert_close("stem4_vs_igemm", y, y_ig.float().cpu(), atol=2e-2 * float(ref.abs().max()), rtol=0)
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 32), (3, 30, 26), (2, 224, 224), (301, 64, 64), (1, 256, 256)])
+def test_stem4_wgrad(cuda, shape):
+    """Dedicated stem weight-gradient kernel (dY row pairs x input row, overlapping no-swizzle B operand)."""
+    from byol_b200 import ops
+    n, h, w = shape
+    g = torch.Generator().manual_seed(31)
+    x = R.bf16_round(torch.rand(n, 3, h, w, generator=g) - 0.3)
+    dy = R.bf16_round(torch.randn(n, h // 2, w // 2, 64, generator=g))
+    xs4 = ops.nchw_to_stem4(x.to(cuda))
+    ref = R.conv_wgrad_ref(x.permute(0, 2, 3, 1).contiguous(), dy, (64, 3, 7, 7), 2, 3)
+    dw = torch.zeros(64, 3, 7, 7, device=cuda)
+    ops.stem_conv_wgrad(xs4, dy.to(cuda, torch.bfloat16), dw, h, w)
+    torch.cuda.synchronize()
+    assert_close("stem4_wgrad", dw, ref, atol=2e-3 * float(ref.abs().max()), rtol=0)
+    ops.stem_conv_wgrad(xs4, dy.to(cuda, torch.bfloat16), dw, h, w)
+    torch.cuda.synchronize()
+    assert_close("stem4_wgrad_acc", dw, 2 * ref, atol=4e-3 * float(ref.abs().max()), rtol=0)
+
+
 def test_conv_dgrad_parity_with_residual(cuda):
     """BasicBlock-style strided 3x3 dgrad with the residual gradient added in the epilogue (parity mode)."""
     from byol_b200 import ops
