@@ -190,6 +190,32 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// Warp-convergent variants: the WHOLE warp executes the call with warp-uniform operands and one elected lane issues.
+// Keeping the issuing warp's control flow convergent lets the compiler hold descriptors in uniform registers; inside
+// an `if (lane == 0)` region it wraps every tcgen05.mma in a uniformisation loop (ELECT / R2UR.BROADCAST / BRA.U.ANY,
+// ~100 cycles per MMA), which is the limit for narrow (N <= 64) MMAs.
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

@@ -145,12 +145,15 @@ stem_fprop_kernel(const __grid_constant__ CUtensorMap tmapY, const StemParams p)
     if (lane == 0) tma_store_wait_all();
   } else if (warp == 8) {
     // ======================= MMA issuer ===================================================
-    if (lane == 0) {
+    // the whole warp runs the loop (uniform control flow and operands); one elected lane issues (see common.cuh)
+    {
       constexpr uint32_t idesc = make_idesc(1u, 128, 64, 0u, 0u);
       mbar_wait(wfull, 0u);
       tc_fence_after_sync();
       const uint32_t w_addr = smem_u32(sW);
       const uint32_t ring_addr = smem_u32(ring);
+      // B: [k-chunk][cout][8]: chunk step 1024, 8-row group step 128; kh block 4096 B, K step (2 chunks) 2048 B
+      const uint64_t bdesc0 = make_smem_desc_none(w_addr, 1024u, 128u);
       int qb = 0, qn = 0, local = 0;
       for (int t = t_begin; t < t_end; ++t, ++local) {
         const int oh = t % p.Ho;
@@ -169,24 +172,28 @@ stem_fprop_kernel(const __grid_constant__ CUtensorMap tmapY, const StemParams p)
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64);
 #pragma unroll
-        for (int kh = 0; kh < 7; ++kh) {
-          const uint32_t a_row = ring_addr + (uint32_t)(((qb + (kh >> 1)) % ST_NP) * ST_PAIR_BYTES + (kh & 1) * ST_ROW_BYTES);
+        for (int kp = 0; kp < 4; ++kp) {   // row pair kp holds kernel rows 2*kp and 2*kp + 1
+          // A: row m = output pixel m, 16-byte chunk c = input pixels 2m + 4s + 2c, +1 -> LBO 16, SBO 128 (overlapping)
+          const uint64_t adesc0 =
+              make_smem_desc_none(ring_addr + (uint32_t)(((qb + kp) % ST_NP) * ST_PAIR_BYTES), 16u, 128u);
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            // A: row m = output pixel m, 16-byte chunk c = input pixels 2m + 4s + 2c, +1 -> LBO 16, SBO 128 (overlapping)
-            const uint64_t adesc = make_smem_desc_none(a_row + 32u * s, 16u, 128u);
-            // B: [k-chunk][cout][8]: chunk step 1024, 8-row group step 128
-            const uint64_t bdesc = make_smem_desc_none(w_addr + (uint32_t)(kh * 4096 + s * 2048), 1024u, 128u);
-            umma_bf16(tmem_d, adesc, bdesc, idesc, (uint32_t)((kh | s) != 0));
+          for (int r = 0; r < 2; ++r) {
+            const int kh = 2 * kp + r;
+            if (kh < 7) {
+#pragma unroll
+              for (int s = 0; s < 2; ++s)
+                umma_bf16_elect(tmem_d, adesc0 + (uint64_t)((r * ST_ROW_BYTES + 32 * s) >> 4),
+                                bdesc0 + (uint64_t)((kh * 4096 + s * 2048) >> 4), idesc, (uint32_t)((kh | s) != 0));
+            }
           }
         }
         const bool last = (t + 1 == t_end) || ((t + 1) % p.Ho == 0);
         if (last) {
-          for (int j = 0; j < 4; ++j) umma_commit(&empty_bar[(qb + j) % ST_NP]);
+          for (int j = 0; j < 4; ++j) umma_commit_elect(&empty_bar[(qb + j) % ST_NP]);
         } else {
-          umma_commit(&empty_bar[qb % ST_NP]);
+          umma_commit_elect(&empty_bar[qb % ST_NP]);
         }
-        umma_commit(&tfull_bar[acc]);
+        umma_commit_elect(&tfull_bar[acc]);
       }
     }
     __syncwarp();
@@ -232,7 +239,7 @@ stem_fprop_kernel(const __grid_constant__ CUtensorMap tmapY, const StemParams p)
 //   D = four TMEM accumulators [128 = 2 kh x 64 co][32 = (kw, c)] (row parity x chain), kept for the CTA's whole
 //     contiguous range of units and added to the fp32 gradient with atomics at the end.
 // The dY ring has 11 slots + a mirror of slot 0 behind slot 10, so that "row oh-1, row oh" are always adjacent in smem.
-//   warps 0-3: final epilogue, warp 4: MMA issuer, warp 5: producer.
+//   warps 0-3: final epilogue, warps 4 and 6: MMA issuers (one per chain), warp 5: producer.
 // ---------------------------------------------------------------------------------------------
 static constexpr int SW_NS = 11;   // 4 rows in use + 7 rows of prefetch (dY streams from HBM: the ring depth hides its latency)
 static constexpr int SW_TILE = 128 * 128;
@@ -260,7 +267,7 @@ __device__ __forceinline__ void tma_load_4d_stem(uint32_t dst_smem, const CUtens
       : "memory");
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(224, 1)
 stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmapDY, const StemWgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -280,9 +287,9 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmapDY, const StemWgradPar
   const int u_end = (int)((int64_t)(blockIdx.x + 1) * p.num_units / gridDim.x);
 
   if (warp == 5 && lane == 0) {
-    for (int s = 0; s < SW_NS; ++s) { mbar_init(&dfull[s], 1u); mbar_init(&dempty[s], 1u); }
-    for (int s = 0; s < SW_NX; ++s) { mbar_init(&xfull[s], 1u); mbar_init(&xempty[s], 1u); }
-    mbar_init(done, 1u);
+    for (int s = 0; s < SW_NS; ++s) { mbar_init(&dfull[s], 1u); mbar_init(&dempty[s], 2u); }   // 2 = both MMA warps
+    for (int s = 0; s < SW_NX; ++s) { mbar_init(&xfull[s], 1u); mbar_init(&xempty[s], 2u); }
+    mbar_init(done, 2u);
     fence_mbar_init();
     tma_prefetch_desc(&tmapDY);
   }
@@ -320,10 +327,14 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmapDY, const StemWgradPar
       }
     }
     __syncwarp();
-  } else if (warp == 4) {
-    // ======================= MMA issuer ===================================================
-    if (lane == 0) {
+  } else if (warp == 4 || warp == 6) {
+    // ======================= MMA issuers (one warp per chain) =============================
+    // N = 32 MMAs take only 16 tensor-core cycles, so instruction issue is the limit: the two chains (independent
+    // accumulators) are issued by two warps, descriptors are built once per unit and advanced by immediates.
+    // the whole warp runs the loop (uniform control flow and operands); one elected lane issues (see common.cuh)
+    {
       constexpr uint32_t idesc = make_idesc(1u, 128, 32, 1u, 1u);   // both operands MN-major
+      const int chain = warp == 4 ? 0 : 1;
       const uint32_t dy_addr = smem_u32(sDY), x_addr = smem_u32(sX);
       int qb = 0, qn = 0, xq = 0;
       uint32_t used = 0;
@@ -342,29 +353,31 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmapDY, const StemWgradPar
         const int xs = xq % SW_NX;
         mbar_wait(&xfull[xs], (uint32_t)((xq / SW_NX) & 1));
         tc_fence_after_sync();
-        const uint32_t xrow = x_addr + (uint32_t)(xs * ST_ROW_BYTES);
+        // chain 0: dY rows (a-1, a) <-> kh = (par+2, par); chain 1: rows (a-3, a-2) <-> kh = (par+6, par+4)
+        const int par = v & 1;
+        const uint32_t tmem_d = tmem_base + (uint32_t)((par * 2 + chain) * 32);
+        const uint32_t tile0 = dy_addr + (uint32_t)(((qb + (chain == 0 ? 2 : 0)) % SW_NS) * SW_TILE);
+        const uint64_t adesc = make_smem_desc_sw128(tile0, (uint32_t)SW_TILE, 1024u);
+        const uint64_t bdesc = make_smem_desc_none(x_addr + (uint32_t)(xs * ST_ROW_BYTES), p.b_lbo, p.b_sbo);
+        const uint32_t acc0 = (used >> par) & 1u;
+        if (p.ksteps == 7) {
 #pragma unroll
-        for (int chain = 0; chain < 2; ++chain) {
-          // chain 0: dY rows (a-1, a) <-> kh = (par+2, par); chain 1: rows (a-3, a-2) <-> kh = (par+6, par+4)
-          const int acc = (v & 1) * 2 + chain;
-          const uint32_t tile0 = dy_addr + (uint32_t)(((qb + (chain == 0 ? 2 : 0)) % SW_NS) * SW_TILE);
-          for (int ks = 0; ks < p.ksteps; ++ks) {
-            const uint64_t adesc = make_smem_desc_sw128(tile0 + (uint32_t)(ks * 2048), (uint32_t)SW_TILE, 1024u);
-            const uint64_t bdesc = make_smem_desc_none(xrow + (uint32_t)(ks * 256), p.b_lbo, p.b_sbo);
-            umma_bf16(tmem_base + (uint32_t)(acc * 32), adesc, bdesc, idesc,
-                      (uint32_t)((((used >> acc) & 1u) != 0u) || ks != 0));
-          }
-          used |= 1u << acc;
+          for (int ks = 0; ks < 7; ++ks)   // K step = 16 pixels: +2048 B in the dY tile, +256 B in the input row
+            umma_bf16_elect(tmem_d, adesc + (uint64_t)(128 * ks), bdesc + (uint64_t)(16 * ks), idesc, ks == 0 ? acc0 : 1u);
+        } else {
+          for (int ks = 0; ks < p.ksteps; ++ks)
+            umma_bf16_elect(tmem_d, adesc + (uint64_t)(128 * ks), bdesc + (uint64_t)(16 * ks), idesc, ks == 0 ? acc0 : 1u);
         }
-        umma_commit(&xempty[xs]);
+        used |= 1u << par;
+        umma_commit_elect(&xempty[xs]);
         const bool last = (u + 1 == u_end) || (v == p.Hp - 1);
         if (last) {
-          for (int j = 0; j < 4; ++j) umma_commit(&dempty[(qb + j) % SW_NS]);
+          for (int j = 0; j < 4; ++j) umma_commit_elect(&dempty[(qb + j) % SW_NS]);
         } else if (v & 1) {
-          umma_commit(&dempty[qb % SW_NS]);
+          umma_commit_elect(&dempty[qb % SW_NS]);
         }
       }
-      umma_commit(done);
+      umma_commit_elect(done);
     }
     __syncwarp();
   } else {
@@ -564,6 +577,6 @@ extern "C" int byol_stem_conv_wgrad(const void* xs, const void* dy, float* dw, i
   }
   int grid = stem_sm_count();
   if (grid > p.num_units) grid = p.num_units;
-  stem_wgrad_kernel<<<grid, 192, SW_TOTAL, stream>>>(tmDY, p);
+  stem_wgrad_kernel<<<grid, 224, SW_TOTAL, stream>>>(tmDY, p);
   return check_launch("stem_wgrad_kernel");
 }
