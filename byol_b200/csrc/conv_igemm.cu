@@ -603,7 +603,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     for (int j = (it > GATHER_LAG ? it - GATHER_LAG : 0); j < it; ++j) mbar_arrive(&full_bar[j % STAGES]);
   } else if (warp == MMA_WARP) {
     // ======================= MMA issuer ===================================================
-    if (lane == 0) {
+    // whole warp, warp-uniform operands, one elected lane issues (umma_*_elect, common.cuh)
+    {
       constexpr uint32_t idesc = make_idesc(1u, BM, BN, 0u, 0u);
       int it = 0, local = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
@@ -622,12 +623,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+            umma_bf16_elect(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                       (uint32_t)((kb | k) != 0));
           }
-          umma_commit(&empty_bar[s]);
+          umma_commit_elect(&empty_bar[s]);
         }
-        umma_commit(&tfull_bar[acc]);
+        umma_commit_elect(&tfull_bar[acc]);
       }
     }
     __syncwarp();
@@ -851,7 +852,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     }
     tc_fence_before_sync();
   } else if (warp == 4) {
-    if (lane == 0) {
+    // whole warp, warp-uniform operands, one elected lane issues (umma_*_elect, common.cuh)
+    {
       constexpr uint32_t idesc = make_idesc(1u, 128, BN, 1u, 1u);  // both operands MN-major
       for (int it = 0; it < nkb; ++it) {
         const int s = it % STAGES;
@@ -864,12 +866,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 #pragma unroll
         for (int k = 0; k < WG_KROWS / 16; ++k) {
           // advance 16 pixel rows = 2048 bytes: +128 in the (addr >> 4) field
-          umma_bf16(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc,
+          umma_bf16_elect(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc,
                     (uint32_t)((it | k) != 0));
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit_elect(&empty_bar[s]);
       }
-      umma_commit(accum_bar);
+      umma_commit_elect(accum_bar);
     }
     __syncwarp();
   } else {

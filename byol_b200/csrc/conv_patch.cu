@@ -223,7 +223,8 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_con
     }
   } else if (warp == 4) {
     // ======================= MMA issuer ===================================================
-    if (lane == 0) {
+    // whole warp, warp-uniform operands, one elected lane issues (umma_*_elect, common.cuh)
+    {
       constexpr uint32_t idesc = make_idesc(1u, 128, BN, 0u, 0u);
       int pit = 0, bit = 0, local = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
@@ -251,14 +252,14 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_con
               const uint32_t tmem_d = tmem_base + (uint32_t)((acc * 2 + jp) * BN);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                umma_bf16_elect(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                           (uint32_t)((cc | tap | k) != 0));
             }
-            umma_commit(&bempty[bs]);
+            umma_commit_elect(&bempty[bs]);
           }
-          umma_commit(&pempty[ps]);
+          umma_commit_elect(&pempty[ps]);
         }
-        umma_commit(&tfull[acc]);
+        umma_commit_elect(&tfull[acc]);
       }
     }
     __syncwarp();
@@ -509,7 +510,8 @@ conv3x3_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmapX, const __gr
     }
     __syncwarp();
   } else if (warp == 4) {
-    if (lane == 0) {
+    // whole warp, warp-uniform operands, one elected lane issues (umma_*_elect, common.cuh)
+    {
       constexpr uint32_t idesc = make_idesc(1u, 128, 64 * NB, 1u, 1u);   // both operands MN-major
       for (int it = 0; it < ntiles; ++it) {
         const int s = it % WP_STAGES;
@@ -525,12 +527,12 @@ conv3x3_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmapX, const __gr
           const uint64_t bdesc = make_smem_desc_sw128(x_base + shift, P_PATCH_SLOT, 1024);
 #pragma unroll
           for (int k = 0; k < 8; ++k)   // 16 pixel rows = 2048 bytes per step
-            umma_bf16(tmem_base + (uint32_t)(kw * 64 * NB), adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k),
+            umma_bf16_elect(tmem_base + (uint32_t)(kw * 64 * NB), adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k),
                       idesc, (uint32_t)((it | k) != 0));
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit_elect(&empty_bar[s]);
       }
-      umma_commit(accum_bar);
+      umma_commit_elect(accum_bar);
     }
     __syncwarp();
   } else {
