@@ -186,8 +186,22 @@ def layer_table(model, batch, image_size, reps=5):
         dw = torch.zeros(cout, cin, k, k, device=dev)
         stats = torch.zeros(2 * cout, device=dev)
         flops = 2.0 * batch * ho * ho * cout * cin * k * k
-        t_f = timed(lambda: ops.conv_fprop(x, wf, k, k, s, p, stats=stats))
-        t_w = timed(lambda: ops.conv_wgrad(x, dy, dw, k, k, s, p))
+        if u is eng.stem and eng.w_online.stem4_ok and ops.stem4_supported(cin, cout, hin, hin, k, s, p):
+            # the engine's stem path: padded NHWC4 image + the dedicated kernels
+            xs4 = ops.nchw_to_stem4(torch.randn(batch, cin, hin, hin, device=dev))
+            t_f = timed(lambda: ops.stem_conv_fprop(xs4, eng.w_online.w_stem4, hin, hin, stats=stats))
+            t_w = timed(lambda: ops.stem_conv_wgrad(xs4, dy, dw, hin, hin))
+            del xs4
+        elif k == 1 and s == 2 and p == 0 and hin % 2 == 0:
+            # the engine's downsample path: compact the strided pixels once, then a plain TMA-fed GEMM (the
+            # compaction is charged to fprop)
+            xsub = ops.subsample2(x)
+            t_f = timed(lambda: ops.conv_fprop(ops.subsample2(x), wf, 1, 1, 1, 0, stats=stats))
+            t_w = timed(lambda: ops.conv_wgrad(xsub, dy, dw, 1, 1, 1, 0))
+            del xsub
+        else:
+            t_f = timed(lambda: ops.conv_fprop(x, wf, k, k, s, p, stats=stats))
+            t_w = timed(lambda: ops.conv_wgrad(x, dy, dw, k, k, s, p))
         t_d = timed(lambda: ops.conv_dgrad(dy, wd, hin, hin, k, k, s, p)) if wd is not None else None
         row = {"cin": cin, "cout": cout, "k": k, "stride": s, "hin": hin, "count": count, "gflop": flops / 1e9,
                "fprop_ms": t_f, "fprop_tflops": flops / t_f / 1e9, "wgrad_ms": t_w, "wgrad_tflops": flops / t_w / 1e9,

@@ -106,6 +106,22 @@ __global__ void prep_weights_multi_kernel(const float* __restrict__ flat, bf16* 
   }
 }
 
+// y[n, i, j, :] = x[n, 2i, 2j, :]: the pixels a 1x1 / stride-2 convolution reads, compacted so that the downsample
+// branch runs as a plain (TMA-fed) GEMM.  One thread per 16-byte vector.
+__global__ void subsample2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C) {
+  const int groups = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const int64_t total = (int64_t)N * Ho * Wo * groups;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    int64_t t = i / groups;
+    const int j = (int)(t % Wo); t /= Wo;
+    const int r = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    reinterpret_cast<uint4*>(y)[i] =
+        __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)n * H + 2 * r) * W + 2 * j) * C) + g);
+  }
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16_rn(x[i]);
@@ -375,6 +391,13 @@ extern "C" int byol_prep_weights_multi(const float* flat, void* pool_f, void* po
   dim3 grid(128, num_units);   // blocks beyond a small unit's size exit at once; the largest (8M elements) need them   // blocks beyond a small unit's size exit at once; the largest (8M elements) need them
   prep_weights_multi_kernel<<<grid, 256, 0, stream>>>(flat, (bf16*)pool_f, (bf16*)pool_d, desc);
   return check_launch("prep_weights_multi_kernel");
+}
+
+extern "C" int byol_subsample2(const void* x, void* y, int N, int H, int W, int C, cudaStream_t stream) {
+  BYOL_CHECK_ARG(x && y && N > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "byol_subsample2: bad args");
+  const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
+  subsample2_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const bf16*)x, (bf16*)y, N, H, W, C);
+  return check_launch("subsample2_kernel");
 }
 
 extern "C" int byol_cast_f32_bf16(const float* x, void* y, int64_t n, cudaStream_t stream) {

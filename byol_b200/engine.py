@@ -256,7 +256,11 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------
     # forward building blocks (lists are per lane)
     # ------------------------------------------------------------------------------------------
-    def _conv_bn(self, u, xs, lanes, train, stem4=None):
+    @staticmethod
+    def _down_as_gemm(u, x):
+        return u.k == 1 and u.stride == 2 and u.pad == 0 and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0
+
+    def _conv_bn(self, u, xs, lanes, train, stem4=None, unit_stride=None):
         """raw conv/linear outputs + BN coefficients [scale, shift, mean, invstd] per lane."""
         L, C = len(lanes), u.cout
         stats = self._zpool.take(L * 2 * C) if train else None
@@ -270,7 +274,7 @@ class Engine(object):
             elif u.kind == "linear":
                 y = ops.linear_fprop(x, wset.wf[u.idx], bias=bias, stats=st)
             else:
-                y = ops.conv_fprop(x, wset.wf[u.idx], u.k, u.k, u.stride, u.pad, stats=st)
+                y = ops.conv_fprop(x, wset.wf[u.idx], u.k, u.k, unit_stride or u.stride, u.pad, stats=st)
             ys.append(y)
         coeffs = self._cpool.take(L * 4 * C).view(L, 4, C)
         bn = u.bn
@@ -319,8 +323,12 @@ class Engine(object):
         # block output: the backward pass reads the ReLU mask as bits (1/16 of the activation's bytes)
         masks = [torch.empty(ylast[i].numel() // 8, dtype=torch.uint8, device=ylast[i].device)
                  if lanes[i][2] is not None else None for i in range(L)]
+        xsub = None
         if b.down is not None:
-            yd, cd = self._conv_bn(b.down, xs, lanes, train)
+            # 1x1 / stride-2 downsample: compact the pixels it reads, then it is a plain TMA-fed GEMM (fprop + wgrad)
+            if self._down_as_gemm(b.down, xs[0]):
+                xsub = [ops.subsample2(x) for x in xs]
+            yd, cd = self._conv_bn(b.down, xsub if xsub is not None else xs, lanes, train, unit_stride=1 if xsub else None)
             outs = [self._apply(ylast[i], clast[i], True, resid=yd[i], rc=cd[i], mask=masks[i]) for i in range(L)]
         else:
             yd, cd = None, None
@@ -328,7 +336,7 @@ class Engine(object):
         for i, (_, _, saved) in enumerate(lanes):
             if saved is not None:
                 saved["blocks"].append({
-                    "mask": masks[i],
+                    "mask": masks[i], "xsub": xsub[i] if xsub is not None else None,
                     "x": xs[i], "y1": y1[i], "c1": c1[i], "a1": a1[i], "y2": y2[i], "c2": c2[i],
                     "a2": a2[i] if a2 is not None else None, "y3": y3[i] if y3 is not None else None,
                     "c3": c3[i] if c3 is not None else None, "yd": yd[i] if yd is not None else None,
@@ -468,33 +476,33 @@ class Engine(object):
             dzs.append(dz)
         return dys, dzs
 
-    def _wgrad(self, u, xs, dys):
+    def _wgrad(self, u, xs, dys, unit_stride=None):
         """dW += dY^T * im2col(X) on the side stream: the weight-gradient GEMMs only feed the flat gradient buffer, so
         they overlap with the HBM-bound BatchNorm-backward kernels of the next layer on the main stream."""
         dw = self._gview(u.w_off, u.w_numel).view(u.cout, u.cin, u.k, u.k)
         main = torch.cuda.current_stream()
         side = self._side_stream
         if side is None:
-            self._launch_wgrad(u, xs, dys, dw)
+            self._launch_wgrad(u, xs, dys, dw, unit_stride)
             return
         ev = torch.cuda.Event()
         ev.record(main)
         side.wait_event(ev)
         with torch.cuda.stream(side):
-            self._launch_wgrad(u, xs, dys, dw)
+            self._launch_wgrad(u, xs, dys, dw, unit_stride)
         # keep the operands alive until the launching stream has joined the side stream (no record_stream: that would
         # add an allocator event per tensor); after the join, reuse by the owning stream is ordered behind the reads
         self._side_refs.append((xs, dys))
         self._side_used = True
 
-    def _launch_wgrad(self, u, xs, dys, dw):
+    def _launch_wgrad(self, u, xs, dys, dw, unit_stride=None):
         for x, dy in zip(xs, dys):
             if isinstance(x, tuple):      # stem: (padded NHWC4 image, H, W) -> dedicated kernel
                 ops.stem_conv_wgrad(x[0], dy, dw, x[1], x[2])
             elif u.kind == "linear":
                 ops.conv_wgrad(x.view(x.shape[0], 1, 1, -1), dy.view(dy.shape[0], 1, 1, -1), dw, 1, 1, 1, 0)
             else:
-                ops.conv_wgrad(x, dy, dw, u.k, u.k, u.stride, u.pad)
+                ops.conv_wgrad(x, dy, dw, u.k, u.k, unit_stride or u.stride, u.pad)
 
     def _join_side_stream(self):
         if self._side_stream is not None and self._side_used:
@@ -530,7 +538,10 @@ class Engine(object):
         resid_masks = None
         if b.down is not None:
             dyd, _ = self._bn_bwd(b.down, gs, [s["yd"] for s in S], [s["cd"] for s in S], 3, acts=masks)
-            self._wgrad(b.down, xs, dyd)
+            if S[0].get("xsub") is not None:
+                self._wgrad(b.down, [s["xsub"] for s in S], dyd, unit_stride=1)
+            else:
+                self._wgrad(b.down, xs, dyd)
             resid = self._dgrad(b.down, dyd, xshapes)
         elif fuse_resid:
             resid, resid_masks = gs, masks

@@ -95,6 +95,15 @@ def stem_conv_wgrad(xs4, dy, dw, h, w):
     return dw
 
 
+def subsample2(x):
+    """x[N,H,W,C] -> x[:, ::2, ::2, :] compacted (H, W even): the input of a 1x1 / stride-2 convolution."""
+    _chk(x, BF16, "x")
+    n, h, w, c = x.shape
+    y = torch.empty((n, h // 2, w // 2, c), dtype=BF16, device=x.device)
+    check(lib.byol_subsample2(_ptr(x), _ptr(y), n, h, w, c, _stream()), "byol_subsample2")
+    return y
+
+
 def prep_weight(w, cpad=None, want_dgrad=True, out_f=None, out_d=None):
     """fp32 [Cout, Cin, KH, KW] (or [out, in] for Linear) -> (w_fprop bf16 [Cout, taps*Cpad], w_dgrad bf16 [Cin, taps*Cout])."""
     _chk(w, F32, "w")

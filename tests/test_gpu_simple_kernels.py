@@ -186,6 +186,15 @@ def test_fused_stem_pool_is_bit_identical(cuda):
     assert torch.equal(y1, y2) and torch.equal(i1, i2)
 
 
+def test_subsample2(cuda):
+    from byol_b200 import ops
+    g = torch.Generator().manual_seed(14)
+    x = torch.randn(3, 10, 14, 64, generator=g).to(cuda, BF)
+    y = ops.subsample2(x)
+    torch.cuda.synchronize()
+    assert torch.equal(y, x[:, ::2, ::2, :].contiguous())
+
+
 def _loss_ref(q1, q2, z1, z2):
     # /root/reference/objective.py:6-25 restated (Frobenius norms of the whole matrices, no per-row normalisation)
     def reg(x, y):
