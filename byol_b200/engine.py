@@ -380,7 +380,9 @@ class Engine(object):
             x8.append(conv[id(a)])
         if rep_bf16_out is None:
             rep_bf16_out = [None] * L
-        two = self.multi_stream and L == 4
+        # under SyncBatchNorm the per-layer all-reduces serialise the lane pairs anyway: run all four lanes lock-step
+        # on one stream there, which halves the number of (latency-bound) NCCL calls
+        two = self.multi_stream and L == 4 and not (self.sync and self.world() > 1)
         groups = [(list(range(0, 2)), self._fwd_streams[0]), (list(range(2, 4)), self._fwd_streams[1])] if two \
             else [(list(range(L)), main)]
         self._fin_events = {} if (two and train) else None
@@ -583,7 +585,7 @@ class Engine(object):
         self.notify_backward()
         L = len(saved)
         main = torch.cuda.current_stream()
-        if not (self.multi_stream and L == 2):
+        if not (self.multi_stream and L == 2) or (self.sync and self.world() > 1):
             self._backward_group(saved, d_reps, d_projs, d_preds)
             return
         ev = torch.cuda.Event()
