@@ -19,7 +19,7 @@ c_double = ctypes.c_double
 
 # name -> argtypes (all functions return int status unless listed in _SPECIAL)
 _SIGNATURES = {
-    "byol_conv_igemm": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,                      # src wt dst resid resid_mask
+    "byol_conv_igemm": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,               # src wt dst resid resid_mask resid_up
                         c_void_p, c_void_p, c_void_p,                                          # bias col_sum col_sqsum
                         c_int, c_int, c_int, c_int, c_int, c_int, c_int,                      # Nimg Hs Ws C Ho Wo Ndim
                         c_int, c_int, c_int, c_int, c_int, c_int, c_int,                      # KH KW stride pad mode ldw ldc

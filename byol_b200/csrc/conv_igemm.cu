@@ -35,6 +35,7 @@ struct ConvGemmParams {
   void* dst;           // output [M, ldc] row-major (bf16 or fp32)
   const bf16* resid;   // optional, [M, ldc] bf16, added in the epilogue
   const uint8_t* resid_mask;   // optional ReLU mask bits over the same [M, ldc] index space: add resid only where set
+  int resid_up;                // 1: resid is [Nimg, Ho/2, Wo/2, ldc] and belongs to the even (h, w) pixels only
   const float* bias;   // optional, [Ndim]
   float* col_sum;      // optional, [Ndim] fp32: += sum over rows of the stored value
   float* col_sqsum;    // optional, [Ndim] fp32: += sum over rows of value^2
@@ -258,6 +259,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       }
       int rows_valid = p.M - mrow0;
       rows_valid = rows_valid < 0 ? 0 : (rows_valid > 32 ? 32 : rows_valid);
+      // residual row of this thread's output row (resid_up: the compact gradient of a stride-2 branch is scattered
+      // to the even pixels of the full-resolution map)
+      bool rvalid = mvalid;
+      int64_t rrow = m;
+      if (p.resid_up) {
+        const int w = m % p.Wo;
+        const int t2 = m / p.Wo;
+        const int h = t2 % p.Ho;
+        const int n = t2 / p.Ho;
+        rvalid = mvalid && ((h | w) & 1) == 0;
+        rrow = ((int64_t)n * (p.Ho >> 1) + (h >> 1)) * (p.Wo >> 1) + (w >> 1);
+      }
       if (WIDE) {
         // the single staging tile of this warp: last tile's TMA store has read it, all lanes finished its statistics
         if (lane == 0) tma_store_wait_read();
@@ -285,9 +298,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           for (int j = 0; j < 32; ++j)
             if (nbase + j < p.Ndim) v[j] += __ldg(p.bias + nbase + j);
         }
-        if (p.resid != nullptr && mvalid) {
-          const bf16* rp = p.resid + (int64_t)m * p.ldc + nbase;
-          const uint8_t* mp = p.resid_mask != nullptr ? p.resid_mask + (((int64_t)m * p.ldc + nbase) >> 3) : nullptr;
+        if (p.resid != nullptr && rvalid) {
+          const bf16* rp = p.resid + rrow * p.ldc + nbase;
+          const uint8_t* mp = p.resid_mask != nullptr ? p.resid_mask + ((rrow * p.ldc + nbase) >> 3) : nullptr;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             if (nbase + j < p.Ndim) {
@@ -998,7 +1011,7 @@ using namespace byol;
 // mode 1 (dgrad):  src coord = (o + pad - k) / stride  (valid only when divisible); here `src` is dY,
 //                  (Hs, Ws) its spatial size and (Ho, Wo) the spatial size of dX.
 extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const void* resid,
-                               const void* resid_mask, const float* bias, float* col_sum, float* col_sqsum, int Nimg, int Hs, int Ws, int C, int Ho, int Wo,
+                               const void* resid_mask, int resid_up, const float* bias, float* col_sum, float* col_sqsum, int Nimg, int Hs, int Ws, int C, int Ho, int Wo,
                                int Ndim, int KH, int KW, int stride, int pad, int mode, int ldw, int ldc,
                                int out_fp32, int relu, int force_gather, cudaStream_t stream) {
   BYOL_CHECK_ARG(src && wt && dst, "byol_conv_igemm: null pointer");
@@ -1012,7 +1025,10 @@ extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const
   BYOL_CHECK_ARG((int64_t)Nimg * Hs * Ws * C < (1ll << 40), "byol_conv_igemm: src too large");
   // 3x3 / stride 1 / pad 1 (fprop and its dgrad): shared-memory patch reuse instead of a 9x re-gather
   BYOL_CHECK_ARG(resid_mask == nullptr || (resid != nullptr && ldc % 8 == 0), "byol_conv_igemm: resid_mask without resid");
-  if (!force_gather && resid_mask == nullptr && Hs == Ho && Ws == Wo && ldw >= 9 * C &&
+  BYOL_CHECK_ARG(!resid_up || (resid != nullptr && resid_mask == nullptr && Ho % 2 == 0 && Wo % 2 == 0 &&
+                               !(mode == 1 && stride == 2)),
+                 "byol_conv_igemm: resid_up needs resid, even output dims and a non-parity mode");
+  if (!force_gather && resid_mask == nullptr && !resid_up && Hs == Ho && Ws == Wo && ldw >= 9 * C &&
       patch_conv_applicable(Hs, Ws, C, Ndim, KH, KW, stride, pad, out_fp32, bias, (int64_t)Nimg * Hs * Ws * C))
     return patch_conv_launch(src, wt, dst, resid, col_sum, col_sqsum, Nimg, Hs, Ws, C, Ndim, ldw, ldc, mode, relu,
                              sm_count(), stream);
@@ -1022,6 +1038,7 @@ extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const
   p.dst = dst;
   p.resid = (const bf16*)resid;
   p.resid_mask = (const uint8_t*)resid_mask;
+  p.resid_up = resid_up ? 1 : 0;
   p.bias = bias;
   p.col_sum = col_sum;
   p.col_sqsum = col_sqsum;

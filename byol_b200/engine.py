@@ -514,14 +514,15 @@ class Engine(object):
             self._side_used = False
             self._side_refs = []
 
-    def _dgrad(self, u, dys, in_shapes, resids=None, resid_masks=None):
+    def _dgrad(self, u, dys, in_shapes, resids=None, resid_masks=None, resid_up=False, unit_stride=None):
         wd = self.w_online.wd[u.idx]
         outs = []
         for i, dy in enumerate(dys):
             n, h, w, _ = in_shapes[i]
-            outs.append(ops.conv_dgrad(dy, wd, h, w, u.k, u.k, u.stride, u.pad,
+            outs.append(ops.conv_dgrad(dy, wd, h, w, u.k, u.k, unit_stride or u.stride, u.pad,
                                        resid=None if resids is None else resids[i],
-                                       resid_mask=None if resid_masks is None else resid_masks[i]))
+                                       resid_mask=None if resid_masks is None else resid_masks[i],
+                                       resid_up=resid_up))
         return outs
 
     def _block_bwd(self, b, S, gs):
@@ -538,13 +539,20 @@ class Engine(object):
         fuse_resid = b.down is None and b.c1.k == 1
         dyl, dzs = self._bn_bwd(last, gs, ylast, clast, 3, acts=masks, want_dz=b.down is None and not fuse_resid)
         resid_masks = None
+        resid_up = False
         if b.down is not None:
             dyd, _ = self._bn_bwd(b.down, gs, [s["yd"] for s in S], [s["cd"] for s in S], 3, acts=masks)
             if S[0].get("xsub") is not None:
                 self._wgrad(b.down, [s["xsub"] for s in S], dyd, unit_stride=1)
             else:
                 self._wgrad(b.down, xs, dyd)
-            resid = self._dgrad(b.down, dyd, xshapes)
+            if S[0].get("xsub") is not None and b.c1.k == 1 and b.c1.stride == 1:
+                # plain GEMM on the strided pixels only; the conv1 dgrad epilogue scatters the compact result to the
+                # even pixels (the 3/4-zero dense gradient map of the downsample branch is never written)
+                resid = self._dgrad(b.down, dyd, [tuple(s["xsub"].shape) for s in S], unit_stride=1)
+                resid_up = True
+            else:
+                resid = self._dgrad(b.down, dyd, xshapes)
         elif fuse_resid:
             resid, resid_masks = gs, masks
         else:
@@ -559,7 +567,7 @@ class Engine(object):
         g1 = self._dgrad(b.c2, dy2, [tuple(s["a1"].shape) for s in S])
         dy1, _ = self._bn_bwd(b.c1, g1, [s["y1"] for s in S], [s["c1"] for s in S], 1)
         self._wgrad(b.c1, xs, dy1)
-        return self._dgrad(b.c1, dy1, xshapes, resids=resid, resid_masks=resid_masks)
+        return self._dgrad(b.c1, dy1, xshapes, resids=resid, resid_masks=resid_masks, resid_up=resid_up)
 
     def _mlp_bwd(self, mlp, S, douts):
         """douts: per lane fp32 or bf16 [b, out] gradient of the MLP output; returns bf16 grads of its input."""

@@ -162,21 +162,23 @@ def conv_fprop(x, w_f, kh, kw, stride, pad, bias=None, resid=None, stats=None, r
         out = torch.empty((n, ho, wo, cout), dtype=F32 if out_fp32 else BF16, device=x.device)
     cs = _ptr(stats)
     cq = (stats.data_ptr() + 4 * cout) if stats is not None else 0
-    check(lib.byol_conv_igemm(_ptr(x), _ptr(w_f), _ptr(out), _ptr(resid), 0, _ptr(bias), cs, cq, n, h, w, c, ho, wo,
+    check(lib.byol_conv_igemm(_ptr(x), _ptr(w_f), _ptr(out), _ptr(resid), 0, 0, _ptr(bias), cs, cq, n, h, w, c, ho, wo,
                               cout, kh, kw, stride, pad, 0, ldw, cout, int(out_fp32), int(relu), int(force_gather),
                               _stream()), "byol_conv_igemm(fprop)")
     return out
 
 
-def conv_dgrad(dy, w_d, h, w, kh, kw, stride, pad, resid=None, out=None, force_gather=False, resid_mask=None):
+def conv_dgrad(dy, w_d, h, w, kh, kw, stride, pad, resid=None, out=None, force_gather=False, resid_mask=None,
+               resid_up=False):
     """dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], w) (+ resid, optionally only where the bits of resid_mask,
-    the uint8 ReLU mask written by bn_apply, are set);  w_d is the dgrad layout [Cin, taps*Cout]."""
+    the uint8 ReLU mask written by bn_apply, are set; resid_up: resid is the compact [N, h/2, w/2, Cin] gradient of a
+    stride-2 branch, added to the even pixels);  w_d is the dgrad layout [Cin, taps*Cout]."""
     _chk(dy, BF16, "dy"); _chk(w_d, BF16, "w_d"); _chk(resid, BF16, "resid"); _chk(resid_mask, torch.uint8, "mask")
     n, ho, wo, cout = dy.shape
     cin, ldw = w_d.shape
     if out is None:
         out = torch.empty((n, h, w, cin), dtype=BF16, device=dy.device)
-    check(lib.byol_conv_igemm(_ptr(dy), _ptr(w_d), _ptr(out), _ptr(resid), _ptr(resid_mask), 0, 0, 0, n, ho, wo, cout, h, w, cin,
+    check(lib.byol_conv_igemm(_ptr(dy), _ptr(w_d), _ptr(out), _ptr(resid), _ptr(resid_mask), int(resid_up), 0, 0, 0, n, ho, wo, cout, h, w, cin,
                               kh, kw, stride, pad, 1, ldw, cin, 0, 0, int(force_gather), _stream()),
           "byol_conv_igemm(dgrad)")
     return out

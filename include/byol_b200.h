@@ -38,9 +38,11 @@ int byol_device_sm_count(void);
  *   mode 1 (dgrad): src = dY [Nimg,Hs,Ws,C=Cout], (Ho,Wo) = spatial size of dX, coordinate = (o + pad - k)/stride
  * wt: bf16 [Ndim, ldw] K-major with k = (kh*KW + kw)*C + c (made by byol_prep_weight).
  * resid_mask (optional, uint8 [M*ldc/8], written by byol_bn_apply): resid is added only where its bit is set, i.e.
- * the epilogue applies the ReLU mask of the residual branch (block backward, torchvision resnet.py Bottleneck.forward). */
+ * the epilogue applies the ReLU mask of the residual branch (block backward, torchvision resnet.py Bottleneck.forward).
+ * resid_up = 1: resid is the COMPACT [Nimg, Ho/2, Wo/2, ldc] gradient of a stride-2 1x1 branch and is added to the
+ * even (h, w) pixels only (the dense, 3/4-zero gradient map of the downsample branch is never written). */
 int byol_conv_igemm(const void* src, const void* wt, void* dst, const void* resid, const void* resid_mask,
-                    const float* bias, float* col_sum, float* col_sqsum, int Nimg, int Hs, int Ws, int C, int Ho, int Wo, int Ndim,
+                    int resid_up, const float* bias, float* col_sum, float* col_sqsum, int Nimg, int Hs, int Ws, int C, int Ho, int Wo, int Ndim,
                     int KH, int KW, int stride, int pad, int mode, int ldw, int ldc, int out_fp32, int relu,
                     int force_gather, byol_stream_t stream);
 

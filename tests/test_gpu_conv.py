@@ -222,6 +222,25 @@ def test_conv_dgrad_masked_residual(cuda, hw, cin, cout):
     assert_close("dgrad_masked_resid", dx, ref, atol=1e-2 * float(ref.abs().max()), rtol=0)
 
 
+@pytest.mark.parametrize("hw,cin,cout", [(14, 256, 64), (10, 64, 128), (8, 512, 256)])
+def test_conv_dgrad_upsampled_residual(cuda, hw, cin, cout):
+    """Down block: 1x1 dgrad + the COMPACT gradient of the stride-2 branch scattered to the even pixels."""
+    from byol_b200 import ops
+    n, k, s, p = 3, 1, 1, 0
+    g = torch.Generator().manual_seed(27)
+    wt = R.bf16_round(torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5)
+    dy = R.bf16_round(torch.randn(n, hw, hw, cout, generator=g))
+    rc = R.bf16_round(torch.randn(n, hw // 2, hw // 2, cin, generator=g))
+    _, w_d = ops.prep_weight(wt.to(cuda), cpad=cin, want_dgrad=True)
+    up = torch.zeros(n, hw, hw, cin)
+    up[:, ::2, ::2, :] = rc
+    ref = R.conv_dgrad_ref(dy, wt, (hw, hw), s, p) + up
+    dx = ops.conv_dgrad(dy.to(cuda, torch.bfloat16), w_d, hw, hw, k, k, s, p, resid=rc.to(cuda, torch.bfloat16),
+                        resid_up=True)
+    torch.cuda.synchronize()
+    assert_close("dgrad_up_resid", dx, ref, atol=1e-2 * float(ref.abs().max()), rtol=0)
+
+
 LINEAR_CASES = [("head1", 64, 2048, 4096), ("head2", 64, 4096, 256), ("cls", 96, 2048, 1000), ("pred1", 200, 256, 4096)]
 
 
