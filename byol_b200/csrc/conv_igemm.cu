@@ -1084,9 +1084,9 @@ extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const
   CUtensorMap ta, tb, tc;
   memset(&ta, 0, sizeof(ta));
   if (make_tmap_2d(&tb, wt, (uint64_t)Ndim, (uint64_t)p.Kg, (uint64_t)ldw, (uint32_t)BN) != 0) return -3;
-  // plain-GEMM tiles with few k-blocks are epilogue-bound: wide (128-byte) output staging, 2-stage operand ring
-  static const int wide_max_kb = [] { const char* e = getenv("BYOL_IGEMM_WIDE_MAX_KB"); return e ? atoi(e) : 0; }();
-  const bool wide = a_tma && BN == 128 && !out_fp32 && p.num_kb <= wide_max_kb;
+  // (a WIDE variant - 128-byte output staging rows with a 2-stage operand ring - was measured slower than narrow
+  // staging with 3 stages for every K >= 128 and equal at K = 64, so it is not dispatched)
+  const bool wide = false;
   if (!out_fp32) {
     if (make_tmap_2d(&tc, dst, (uint64_t)p.M, (uint64_t)Ndim, (uint64_t)ldc, 32u, wide ? 64u : 32u) != 0) return -3;
   } else {
@@ -1098,7 +1098,6 @@ extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const
     ta = tb;
   }
   if (BN == 128) {
-    if (wide) return launch_igemm<128, 2, true, true>(ta, tb, tc, p, tiles_m, stream);
     return a_tma ? launch_igemm<128, 3, true, false>(ta, tb, tc, p, tiles_m, stream)
                  : launch_igemm<128, 3, false, false>(ta, tb, tc, p, tiles_m, stream);
   }

@@ -555,9 +555,9 @@ extern "C" int byol_stem_conv_wgrad(const void* xs, const void* dy, float* dw, i
   p.num_units = N * Hp;
   p.ksteps = (Wo + 15) / 16;
   // no-swizzle MN-major B: LBO = step between 8-pixel (K) groups, SBO = step between 16-byte N chunks
-  static const int variant = [] { const char* e = getenv("BYOL_STEM_WGRAD_VARIANT"); return e ? atoi(e) : 0; }();
-  p.b_lbo = variant == 0 ? 128u : 16u;
-  p.b_sbo = variant == 0 ? 16u : 128u;
+  // (for no-swizzle MN-major operands the roles are swapped w.r.t. K-major: measured, the swapped assignment fails)
+  p.b_lbo = 128u;
+  p.b_sbo = 16u;
   PFN_encodeTiledStem fn = stem_encode_fn();
   if (fn == nullptr) { set_last_error("byol_stem_conv_wgrad: cuTensorMapEncodeTiled unavailable"); return -3; }
   CUtensorMap tmDY;
