@@ -90,13 +90,27 @@ def test_bn_statistic_combination_matches_global_batch():
     np.testing.assert_allclose(var.numpy(), full.var(0, unbiased=False).numpy(), rtol=1e-4, atol=1e-6)
 
 
-def test_lr_schedule_first_epoch_is_zero():
-    """Q11: lr = 0.2 * 4096/256 = 3.2, linear warm-up over 10 epochs starting AT 0, then cosine."""
+def test_lr_schedule_matches_reference_wiring():
+    """f2: the closed-form per-epoch schedule reproduces the learning rates of the reference's own wiring
+    (main.build_lr_schedule + optimizers/scheduler.py, recorded by tests/golden/make_golden.py) — including Q11:
+    lr = 0.2 * 4096/256 = 3.2, linear warm-up over 10 epochs starting AT 0, then cosine."""
+    import os
     from byol_b200.wiring import build_optimizer
-    from byol_b200.scheduler import build_lr_schedule
+    from byol_b200.schedule import EpochSchedule
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lr_schedule.npz"))
+    for tag, kind in (("cosine_w10_e40", "cosine"), ("fixed_w3_e12", "fixed"), ("cosine_w0_e8", "cosine")):
+        epochs, warmup = [int(v) for v in z[tag + "_cfg"]]
+        p = torch.nn.Parameter(torch.zeros(4))
+        opt = torch.optim.SGD([p], lr=0.2, momentum=0.9)
+        sched = EpochSchedule(opt, epochs, warmup, kind)
+        lrs = []
+        for _ in range(epochs):
+            lrs.append(opt.param_groups[0]["lr"])
+            sched.step()
+        np.testing.assert_allclose(lrs, z[tag], rtol=1e-12, atol=1e-15, err_msg=tag)
     net = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.BatchNorm1d(4))
-    opt = build_optimizer(net, base_lr=0.2, global_batch_size=4096)
-    sched = build_lr_schedule(opt, epochs=100, warmup=10)
+    opt = build_optimizer(net, base_lr=0.2, global_batch_size=4096)       # wraps SGD in byol_b200.LARS
+    sched = EpochSchedule(opt, epochs=100, warmup=10)
     lrs = []
     for _ in range(14):
         lrs.append(opt.param_groups[0]["lr"])
@@ -104,5 +118,7 @@ def test_lr_schedule_first_epoch_is_zero():
     assert lrs[0] == 0.0                                        # the whole first epoch trains with lr = 0
     np.testing.assert_allclose(lrs[1:11], [0.32 * i for i in range(1, 11)], rtol=1e-12)
     assert abs(lrs[10] - 3.2) < 1e-12 and lrs[12] < lrs[11] <= 3.2   # then cosine decay
-    sd = sched.state_dict()
-    assert set(sd.keys()) == {"warmup", "sched"}
+    st = sched.state_dict()
+    sched2 = EpochSchedule(opt, epochs=100, warmup=10)
+    sched2.load_state_dict(st)
+    assert sched2.get_last_lr() == sched.get_last_lr()
