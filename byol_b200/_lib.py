@@ -30,11 +30,9 @@ _SIGNATURES = {
     "byol_prep_weight_stem4": [c_void_p, c_void_p, c_int, c_void_p],
     "byol_stem_conv_fprop": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "byol_stem_conv_wgrad": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
-    "byol_conv_wgrad": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+    "byol_conv_wgrad": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                         c_int, c_int, c_int, c_int, c_int, c_void_p],
     "byol_bn_stats": [c_void_p, c_void_p, c_int, c_int, c_void_p],
-    "byol_bn_finalize": [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p,
-                         c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "byol_bn_finalize_lanes": [c_void_p, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_int, c_void_p],
     "byol_bn_eval_coeffs": [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p],
@@ -51,6 +49,7 @@ _SIGNATURES = {
     "byol_prep_weights_multi": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "byol_subsample2": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "byol_cast_f32_bf16": [c_void_p, c_void_p, c_int64, c_void_p],
+    "byol_cast_f32_bf16_2d": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "byol_maxpool_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "byol_bn_relu_maxpool_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p],
@@ -62,7 +61,10 @@ _SIGNATURES = {
                       c_void_p],
     "byol_ema_update": [c_void_p, c_void_p, c_float, c_float, c_int64, c_void_p],
     "byol_lars_sgd_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                           c_void_p, c_int, c_void_p, c_float, c_float, c_float, c_int, c_void_p],
+                           c_void_p, c_void_p, c_int, c_void_p, c_float, c_float, c_float, c_int, c_void_p],
+    "byol_ce_topk_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                         c_void_p],
+    "byol_ce_bwd": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "byol_abi_version": [],
     "byol_device_sm_count": [],
 }

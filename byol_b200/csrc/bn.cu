@@ -63,32 +63,7 @@ __global__ void bn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ 
   }
 }
 
-// stats[0:C] = sum, stats[C:2C] = sqsum (global over `count` rows)
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, float momentum, float eps,
-                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
-                                   float* __restrict__ invstd_out, int C) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double mean = (double)stats[c] / count;
-  double var = (double)stats[C + c] / count - mean * mean;   // biased
-  if (var < 0.0) var = 0.0;
-  float invstd = (float)(1.0 / sqrt(var + (double)eps));
-  float g = gamma[c], b = beta[c];
-  float sc = g * invstd;
-  scale[c] = sc;
-  shift[c] = b - (float)mean * sc;
-  mean_out[c] = (float)mean;
-  invstd_out[c] = invstd;
-  if (running_mean != nullptr) {
-    double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
-  }
-}
-
-// Same for up to 4 "lanes" (forward passes that ran this layer in lock-step, each with its own gamma/beta set and
+// Statistics -> coefficients for up to 4 "lanes" (forward passes that ran this layer in lock-step, each with its own gamma/beta set and
 // its own batch statistics) in ONE launch; the running statistics are updated lane after lane, i.e. in the order
 // the reference's four sequential forward passes would update them (main.py:244-247).
 struct LanePtrs { const float* p[4]; };
@@ -332,28 +307,43 @@ __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __r
       sc[e] = MASK == 1 ? scale[gi * 8 + e] : 0.f;
       sh[e] = MASK == 1 ? shift[gi * 8 + e] : 0.f;
     }
-    for (int r = row_begin + rlane; r < row_end; r += row_lanes) {
-      const int64_t off = ((int64_t)r * C + gi * 8) >> 3;
-      float gv[8], xv[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(g) + off), gv);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(x) + off), xv);
-      if (MASK == 3) {
-        const uint32_t mb = __ldg(reinterpret_cast<const uint8_t*>(act) + off);
+    // four rows per iteration, all loads issued before the arithmetic (memory-level parallelism: the loop carries
+    // only the accumulators); rows past the end contribute zeros
+    for (int r = row_begin + rlane; r < row_end; r += 4 * row_lanes) {
+      uint4 gq[4], xq[4], aq[4];
+      uint32_t mb[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) gv[e] = ((mb >> e) & 1u) ? gv[e] : 0.f;
-      } else if (MASK == 2) {
-        float av[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(act) + off), av);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) gv[e] = av[e] > 0.f ? gv[e] : 0.f;
-      } else if (MASK == 1) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) gv[e] = (xv[e] * sc[e] + sh[e]) > 0.f ? gv[e] : 0.f;
+      for (int u = 0; u < 4; ++u) {
+        const int rr = r + u * row_lanes;
+        const bool ok = rr < row_end;
+        const int64_t off = ((int64_t)(ok ? rr : r) * C + gi * 8) >> 3;
+        gq[u] = ok ? __ldg(reinterpret_cast<const uint4*>(g) + off) : make_uint4(0u, 0u, 0u, 0u);
+        xq[u] = __ldg(reinterpret_cast<const uint4*>(x) + off);
+        if (MASK == 3) mb[u] = __ldg(reinterpret_cast<const uint8_t*>(act) + off);
+        if (MASK == 2) aq[u] = __ldg(reinterpret_cast<const uint4*>(act) + off);
       }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        a1[e] += gv[e];
-        a2[e] += gv[e] * (xv[e] - mu[e]) * is[e];
+      for (int u = 0; u < 4; ++u) {
+        float gv[8], xv[8];
+        unpack8(gq[u], gv);
+        unpack8(xq[u], xv);
+        if (MASK == 3) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) gv[e] = ((mb[u] >> e) & 1u) ? gv[e] : 0.f;
+        } else if (MASK == 2) {
+          float av[8];
+          unpack8(aq[u], av);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) gv[e] = av[e] > 0.f ? gv[e] : 0.f;
+        } else if (MASK == 1) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) gv[e] = (xv[e] * sc[e] + sh[e]) > 0.f ? gv[e] : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          a1[e] += gv[e];
+          a2[e] += gv[e] * (xv[e] - mu[e]) * is[e];
+        }
       }
     }
 #pragma unroll
@@ -466,16 +456,6 @@ extern "C" int byol_bn_stats(const void* x, float* stats, int M, int C, cudaStre
   return check_launch("bn_stats_kernel");
 }
 
-extern "C" int byol_bn_finalize(const float* stats, double count, const float* gamma, const float* beta,
-                                float* running_mean, float* running_var, float momentum, float eps, float* scale,
-                                float* shift, float* mean, float* invstd, int C, cudaStream_t stream) {
-  BYOL_CHECK_ARG(stats && gamma && beta && scale && shift && mean && invstd && C > 0 && count > 0,
-                 "byol_bn_finalize: bad args");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(stats, count, gamma, beta, running_mean, running_var,
-                                                         momentum, eps, scale, shift, mean, invstd, C);
-  return check_launch("bn_finalize_kernel");
-}
-
 // stats: [L][2C]; coeffs: [L][4][C]; gamma_l / beta_l for l < L (L <= 4)
 extern "C" int byol_bn_finalize_lanes(const float* stats, double count, int L, const float* gamma0, const float* beta0,
                                       const float* gamma1, const float* beta1, const float* gamma2,
@@ -536,6 +516,16 @@ extern "C" int byol_bn_bwd_reduce(const void* g, const void* x, const void* act,
   if (rows_per_block < 32) rows_per_block = 32;
   const int blocks = (M + rows_per_block - 1) / rows_per_block;
   const bf16 *gp = (const bf16*)g, *xp = (const bf16*)x, *ap = (const bf16*)act;
+  const size_t red_bytes = 2 * (size_t)C * sizeof(float);
+  if (red_bytes > 48 * 1024) {   // very wide BatchNorm1d (head_latent_size >= 6144): opt in to > 48 KB of dynamic smem
+    BYOL_CHECK_ARG(red_bytes <= 200 * 1024, "byol_bn_bwd_reduce: C=%d too wide", C);
+    cudaError_t e = cudaSuccess;
+    if (mask_mode == 0) e = cudaFuncSetAttribute(bn_bwd_reduce_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_bytes);
+    else if (mask_mode == 1) e = cudaFuncSetAttribute(bn_bwd_reduce_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_bytes);
+    else if (mask_mode == 2) e = cudaFuncSetAttribute(bn_bwd_reduce_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_bytes);
+    else e = cudaFuncSetAttribute(bn_bwd_reduce_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_bytes);
+    if (e != cudaSuccess) { set_last_error("byol_bn_bwd_reduce: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return -2; }
+  }
   if (mask_mode == 0)
     bn_bwd_reduce_kernel<0><<<blocks, 256, 2 * C * sizeof(float), stream>>>(gp, xp, ap, scale, shift, mean, invstd, s12, s12 + C, M, C, rows_per_block);
   else if (mask_mode == 1)

@@ -25,11 +25,29 @@ int check_launch(const char* what) {
   return 0;
 }
 
+int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev < kMaxDevices ? dev : kMaxDevices - 1;
+}
+
+int device_sm_count() {
+  static int n[kMaxDevices] = {};
+  const int slot = device_slot();
+  if (n[slot] == 0) {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[slot] = v;
+  }
+  return n[slot];
+}
+
 }  // namespace byol
 
 extern "C" const char* byol_last_error(void) { return byol::g_last_error; }
 
-extern "C" int byol_abi_version(void) { return 1; }
+extern "C" int byol_abi_version(void) { return 2; }
 
 // number of SMs of the current device (used by the host side to size persistent grids); < 0 on error
 extern "C" int byol_device_sm_count(void) {

@@ -17,6 +17,12 @@ typedef __nv_bfloat16 bf16;
 void set_last_error(const char* fmt, ...);
 int check_launch(const char* what);
 
+// One process may drive several GPUs: per-kernel attributes (cudaFuncSetAttribute) and the SM count are per device,
+// so the host wrappers cache them per device slot (capi.cu).
+static constexpr int kMaxDevices = 64;
+int device_slot();       // current CUDA device index, clamped to [0, kMaxDevices)
+int device_sm_count();   // SM count of the current device (cached per device; 148 if the query fails)
+
 #define BYOL_CHECK_ARG(cond, ...)                 \
   do {                                            \
     if (!(cond)) {                                \
@@ -167,18 +173,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// same, tf32 inputs (fp32 storage)
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");

@@ -90,16 +90,14 @@ __device__ __forceinline__ TileInfo tile_info(const ConvGemmParams& p, int tile,
 // Epilogue geometry.  The TMA-operand variant (plain GEMM: 1x1 / stride 1 convolutions and the MLP layers) has no
 // gather warps and is bound by its epilogue (few k-blocks per tile, outputs up to 4x the inputs), so it runs EIGHT
 // epilogue warps: warps w and w + 4 share TMEM lane quarter w & 3 and split the tile's columns.
-//   WIDE (BN = 128, 8 warps): each warp stages its [32 rows][64 cols] as 128-byte swizzled rows and issues ONE TMA
-//   store per tile (full 128-byte row segments in global memory); 32 KB of staging, so the operand ring has 2 stages.
-//   narrow: [32 rows][32 cols] chunks with the 64-byte swizzle, NBUF staging buffers per warp.
-template <int BN, int STAGES, bool A_TMA, bool WIDE>
+// Output staging: [32 rows][32 cols] chunks with the 64-byte swizzle, NBUF staging buffers per warp.  (A variant with
+// 128-byte staging rows and a 2-stage operand ring was measured slower for every K >= 128 and removed.)
+template <int BN, int STAGES, bool A_TMA>
 struct SmemLayout {
   static constexpr int EW = A_TMA ? 8 : 4;                // epilogue warps
   static constexpr int CPW = (BN / 32) / (EW / 4);        // 32-column chunks per epilogue warp
   static constexpr int NBUF = (A_TMA && BN == 128) ? 1 : 2;
-  static constexpr int STAGE_PER_WARP = WIDE ? 4096 : NBUF * 2048;
-  static_assert(!WIDE || CPW == 2, "wide staging = 64 columns per warp");
+  static constexpr int STAGE_PER_WARP = NBUF * 2048;
   static constexpr int B_STAGE_BYTES = BN * 128;
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
@@ -112,27 +110,6 @@ struct SmemLayout {
   static_assert(TOTAL <= 115712, "two CTAs per SM need <= 113 KB of dynamic shared memory each");
 };
 
-// Same for a wide staging tile ([32 rows][128 B], 16-byte chunk c of row r at c ^ (r & 7)): lane -> columns
-// 2*lane, 2*lane + 1 over all 32 rows (one full row per warp-wide load).
-__device__ __forceinline__ void stats_wide(uint32_t stage_base, int lane, int rows_valid, uint64_t& s1, uint64_t& s2) {
-  const uint32_t c = (uint32_t)lane >> 2, wq = (uint32_t)lane & 3u;
-  uint32_t offq[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) offq[q] = stage_base + ((c ^ (uint32_t)q) << 4) + wq * 4u;
-  uint64_t a1 = 0ull, a2 = 0ull, b1 = 0ull, b2 = 0ull;
-  if (rows_valid == 32) {
-#pragma unroll
-    for (int r = 0; r < 32; r += 2) {
-      stat_acc(lds32(offq[r & 7] + (uint32_t)r * 128u), a1, a2);
-      stat_acc(lds32(offq[(r + 1) & 7] + (uint32_t)(r + 1) * 128u), b1, b2);
-    }
-  } else {
-    for (int r = 0; r < rows_valid; ++r) stat_acc(lds32(offq[r & 7] + (uint32_t)r * 128u), a1, a2);
-  }
-  s1 = f2_add(s1, f2_add(a1, b1));
-  s2 = f2_add(s2, f2_add(a2, b2));
-}
-
 // ---------------------------------------------------------------------------------------------
 // fprop / dgrad kernel — persistent: each CTA loops over output tiles (tile = blockIdx.x + i*gridDim.x,
 // n-tile fastest so that concurrently running CTAs share the A tile through L2).  The smem operand ring and
@@ -143,11 +120,11 @@ __device__ __forceinline__ void stats_wide(uint32_t stage_base, int lane, int ro
 //   next warp           : MMA issuer (+ TMEM alloc / dealloc)
 //   last warp           : barrier init + TMA producer
 // ---------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool A_TMA, bool WIDE>
+template <int BN, int STAGES, bool A_TMA>
 __global__ void __launch_bounds__(320, 2)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                   const __grid_constant__ CUtensorMap tmapC, const ConvGemmParams p, const int num_tiles) {
-  using L = SmemLayout<BN, STAGES, A_TMA, WIDE>;
+  using L = SmemLayout<BN, STAGES, A_TMA>;
   constexpr int EW = L::EW;
   constexpr int CPW = L::CPW;
   constexpr int MMA_WARP = 8;
@@ -202,7 +179,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     const int col_w0 = (warp >> 2) * (CPW * 32);  // first tile column of this warp
     const uint32_t stage_base0 = smem_u32(stage_out + warp * L::STAGE_PER_WARP);
     int sbuf = 0;
-    constexpr int NACC = WIDE ? 1 : CPW;
+    constexpr int NACC = CPW;
     uint64_t cs1[NACC], cs2[NACC];   // packed {even, odd} column sums / sums of squares
 #pragma unroll
     for (int i = 0; i < NACC; ++i) { cs1[i] = 0ull; cs2[i] = 0ull; }
@@ -212,19 +189,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 #pragma unroll
       for (int i = 0; i < NACC; ++i) {
         float2 a = f2_unpack(cs1[i]), b = f2_unpack(cs2[i]);
-        int col;
-        bool owner = true;
-        if (WIDE) {
-          col = stat_n0 + col_w0 + 2 * lane;
-        } else {
-          // lanes l and l ^ 16 hold the two row parities of the same column pair
-          a.x += __shfl_xor_sync(0xffffffffu, a.x, 16);
-          a.y += __shfl_xor_sync(0xffffffffu, a.y, 16);
-          b.x += __shfl_xor_sync(0xffffffffu, b.x, 16);
-          b.y += __shfl_xor_sync(0xffffffffu, b.y, 16);
-          col = stat_n0 + col_w0 + i * 32 + 2 * (lane & 15);
-          owner = lane < 16;
-        }
+        // lanes l and l ^ 16 hold the two row parities of the same column pair
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, 16);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, 16);
+        b.x += __shfl_xor_sync(0xffffffffu, b.x, 16);
+        b.y += __shfl_xor_sync(0xffffffffu, b.y, 16);
+        const int col = stat_n0 + col_w0 + i * 32 + 2 * (lane & 15);
+        const bool owner = lane < 16;
         if (owner && col < p.Ndim) {   // Ndim is a multiple of 8: col + 1 is valid too
           atomicAdd(p.col_sum + col, a.x);
           atomicAdd(p.col_sum + col + 1, a.y);
@@ -270,11 +241,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         const int n = t2 / p.Ho;
         rvalid = mvalid && ((h | w) & 1) == 0;
         rrow = ((int64_t)n * (p.Ho >> 1) + (h >> 1)) * (p.Wo >> 1) + (w >> 1);
-      }
-      if (WIDE) {
-        // the single staging tile of this warp: last tile's TMA store has read it, all lanes finished its statistics
-        if (lane == 0) tma_store_wait_read();
-        __syncwarp();
       }
 #pragma unroll
       for (int cl = 0; cl < CPW; ++cl) {
@@ -339,25 +305,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         } else if (p.out_fp32) {
           if (mvalid) {
             float* op = reinterpret_cast<float*>(p.dst) + (int64_t)m * p.ldc + nbase;
+            const bool vec = (p.ldc & 3) == 0;   // 16-byte aligned rows; otherwise (e.g. a 10-class classifier) scalar
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (nbase + j < p.Ndim)
+            for (int j = 0; j < 32; j += 4) {
+              if (vec && nbase + j + 3 < p.Ndim) {
                 *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-        } else if (WIDE) {
-          // row = lane, 16-byte chunk c = 4*cl + j at (c ^ (row & 7)) (= the TMA 128-byte swizzle; the 8 lanes of a
-          // store phase hit 8 different 16-byte slots)
+              } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 q;
-            q.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-            q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-            q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-            q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-            const uint32_t off = (uint32_t)lane * 128u + (uint32_t)(((cl * 4 + j) ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_base0 + off), "r"(q.x), "r"(q.y),
-                         "r"(q.z), "r"(q.w)
-                         : "memory");
+                for (int e = 0; e < 4; ++e)
+                  if (nbase + j + e < p.Ndim) op[j + e] = v[j + e];
+              }
+            }
           }
         } else {
           // stage this warp's [32 rows][32 cols] bf16 block: row = lane, 16-byte chunk j at (j ^ ((row >> 1) & 3))
@@ -387,15 +345,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           if (do_stats) stats_narrow(stage_base, lane, rows_valid, cs1[cl], cs2[cl]);
           if (L::NBUF == 2) sbuf ^= 1;
         }
-      }
-      if (WIDE && n0 + col_w0 < p.Ndim) {
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tmapC, stage_base0, n0 + col_w0, mrow0);   // [32 rows][64 cols], clipped at M / Ndim
-          tma_store_commit();
-        }
-        if (do_stats) stats_wide(stage_base0, lane, rows_valid, cs1[0], cs2[0]);
       }
     }
     if (do_stats && stat_n0 >= 0) flush_stats();
@@ -971,29 +920,22 @@ bool patch_wgrad_applicable(int H, int W, int C, int Cin_real, int Cout, int KH,
 int patch_wgrad_launch(const void* x, const void* dy, float* dw, int Nimg, int H, int W, int C, int Cout, int sms,
                        cudaStream_t stream);
 
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
+static int sm_count() { return device_sm_count(); }
 
-template <int BN, int STAGES, bool A_TMA, bool WIDE>
+template <int BN, int STAGES, bool A_TMA>
 static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                         const ConvGemmParams& p, int tiles_m, cudaStream_t stream) {
-  using L = SmemLayout<BN, STAGES, A_TMA, WIDE>;
-  auto kern = conv_igemm_kernel<BN, STAGES, A_TMA, WIDE>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  using L = SmemLayout<BN, STAGES, A_TMA>;
+  auto kern = conv_igemm_kernel<BN, STAGES, A_TMA>;
+  static bool attr_set[kMaxDevices] = {};
+  const int dev_slot = device_slot();
+  if (!attr_set[dev_slot]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) {
       set_last_error("cudaFuncSetAttribute(conv_igemm) failed: %s", cudaGetErrorString(e));
       return -2;
     }
-    attr_set = true;
+    attr_set[dev_slot] = true;
   }
   const int num_tiles = tiles_m * p.tiles_n;
   int grid = 2 * sm_count();           // persistent: two CTAs per SM (smem and TMEM sized for it)
@@ -1016,8 +958,11 @@ extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const
                                int out_fp32, int relu, int force_gather, cudaStream_t stream) {
   BYOL_CHECK_ARG(src && wt && dst, "byol_conv_igemm: null pointer");
   BYOL_CHECK_ARG(C % 8 == 0 && C >= 8, "byol_conv_igemm: C=%d must be a multiple of 8", C);
-  BYOL_CHECK_ARG(Ndim % 8 == 0, "byol_conv_igemm: Ndim=%d must be a multiple of 8", Ndim);
-  BYOL_CHECK_ARG(ldc % 8 == 0 && ldc >= Ndim, "byol_conv_igemm: bad ldc=%d", ldc);
+  // bf16 outputs are TMA-stored (16-byte row pitch); fp32 outputs (logits, MLP outputs) may have any width
+  BYOL_CHECK_ARG(Ndim > 0 && (Ndim % 8 == 0 || (out_fp32 && resid == nullptr && col_sum == nullptr)),
+                 "byol_conv_igemm: Ndim=%d must be a multiple of 8 (any width only for plain fp32 outputs)", Ndim);
+  BYOL_CHECK_ARG(ldc >= Ndim && (ldc % 8 == 0 || out_fp32), "byol_conv_igemm: bad ldc=%d", ldc);
+  BYOL_CHECK_ARG(!(out_fp32 && col_sum != nullptr), "byol_conv_igemm: fused statistics need a bf16 output");
   BYOL_CHECK_ARG(stride == 1 || stride == 2, "byol_conv_igemm: stride %d unsupported", stride);
   BYOL_CHECK_ARG(mode == 0 || mode == 1, "byol_conv_igemm: bad mode %d", mode);
   const int64_t M64 = (int64_t)Nimg * Ho * Wo;
@@ -1084,11 +1029,8 @@ extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const
   CUtensorMap ta, tb, tc;
   memset(&ta, 0, sizeof(ta));
   if (make_tmap_2d(&tb, wt, (uint64_t)Ndim, (uint64_t)p.Kg, (uint64_t)ldw, (uint32_t)BN) != 0) return -3;
-  // (a WIDE variant - 128-byte output staging rows with a 2-stage operand ring - was measured slower than narrow
-  // staging with 3 stages for every K >= 128 and equal at K = 64, so it is not dispatched)
-  const bool wide = false;
   if (!out_fp32) {
-    if (make_tmap_2d(&tc, dst, (uint64_t)p.M, (uint64_t)Ndim, (uint64_t)ldc, 32u, wide ? 64u : 32u) != 0) return -3;
+    if (make_tmap_2d(&tc, dst, (uint64_t)p.M, (uint64_t)Ndim, (uint64_t)ldc, 32u, 32u) != 0) return -3;
   } else {
     tc = tb;
   }
@@ -1098,11 +1040,11 @@ extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const
     ta = tb;
   }
   if (BN == 128) {
-    return a_tma ? launch_igemm<128, 3, true, false>(ta, tb, tc, p, tiles_m, stream)
-                 : launch_igemm<128, 3, false, false>(ta, tb, tc, p, tiles_m, stream);
+    return a_tma ? launch_igemm<128, 3, true>(ta, tb, tc, p, tiles_m, stream)
+                 : launch_igemm<128, 3, false>(ta, tb, tc, p, tiles_m, stream);
   }
-  return a_tma ? launch_igemm<64, 3, true, false>(ta, tb, tc, p, tiles_m, stream)
-               : launch_igemm<64, 4, false, false>(ta, tb, tc, p, tiles_m, stream);
+  return a_tma ? launch_igemm<64, 3, true>(ta, tb, tc, p, tiles_m, stream)
+               : launch_igemm<64, 4, false>(ta, tb, tc, p, tiles_m, stream);
 }
 
 template <int BN, bool B_TMA>
@@ -1111,30 +1053,35 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, const Wgra
   constexpr int STAGES = 4;
   constexpr int SMEM = STAGES * (WG_A_STAGE + (BN / 64) * WG_KROWS * 128) + 256 + 1024;
   auto kern = conv_wgrad_kernel<BN, STAGES, B_TMA>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  const int dev_slot = device_slot();
+  if (!attr_set[dev_slot]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) {
       set_last_error("cudaFuncSetAttribute(conv_wgrad) failed: %s", cudaGetErrorString(e));
       return -2;
     }
-    attr_set = true;
+    attr_set[dev_slot] = true;
   }
   kern<<<grid, 192, SMEM, stream>>>(ta, tb, p);
   return check_launch("conv_wgrad_kernel");
 }
 
 // dW[Cout][Cin_real][KH][KW] (fp32) += dY^T x gather(src);  dy: [M, Cout] bf16, src: NHWC [Nimg,Hs,Ws,C]
+// ldy: row pitch of dy in elements (0 = Cout); a pitch > Cout lets Cout be any width (TMA zero-fills the columns
+// beyond Cout), e.g. the gradient of a 10-class classifier stored with a pitch of 16.
 extern "C" int byol_conv_wgrad(const void* src, const void* dy, float* dw, int Nimg, int Hs, int Ws, int C,
-                               int Cin_real, int Ho, int Wo, int Cout, int KH, int KW, int stride, int pad,
+                               int Cin_real, int Ho, int Wo, int Cout, int ldy, int KH, int KW, int stride, int pad,
                                int force_gather, cudaStream_t stream) {
   BYOL_CHECK_ARG(src && dy && dw, "byol_conv_wgrad: null pointer");
-  BYOL_CHECK_ARG(C % 8 == 0 && Cout % 8 == 0, "byol_conv_wgrad: C=%d, Cout=%d must be multiples of 8", C, Cout);
+  if (ldy == 0) ldy = Cout;
+  BYOL_CHECK_ARG(C % 8 == 0 && ldy % 8 == 0 && ldy >= Cout && Cout > 0,
+                 "byol_conv_wgrad: C=%d and the dy pitch %d must be multiples of 8 (Cout=%d)", C, ldy, Cout);
   BYOL_CHECK_ARG(Cin_real <= C, "byol_conv_wgrad: Cin_real > C");
   const int64_t M64 = (int64_t)Nimg * Ho * Wo;
   BYOL_CHECK_ARG(M64 > 0 && M64 < (1ll << 31), "byol_conv_wgrad: M out of range");
   // 3x3 / stride 1 / pad 1: shifted-window kernel over TMA patches (no gather)
-  if (!force_gather && Hs == Ho && Ws == Wo && patch_wgrad_applicable(Hs, Ws, C, Cin_real, Cout, KH, KW, stride, pad))
+  if (!force_gather && ldy == Cout && Hs == Ho && Ws == Wo && patch_wgrad_applicable(Hs, Ws, C, Cin_real, Cout, KH, KW, stride, pad))
     return patch_wgrad_launch(src, dy, dw, Nimg, Hs, Ws, C, Cout, sm_count(), stream);
   WgradParams p;
   memset(&p, 0, sizeof(p));
@@ -1174,7 +1121,7 @@ extern "C" int byol_conv_wgrad(const void* src, const void* dy, float* dw, int N
 
   BYOL_CHECK_ARG(!b_tma || C % 8 == 0, "byol_conv_wgrad: bad C");
   CUtensorMap ta, tb;
-  if (make_tmap_2d(&ta, dy, (uint64_t)p.M, (uint64_t)Cout, (uint64_t)Cout, (uint32_t)WG_KROWS) != 0) return -3;
+  if (make_tmap_2d(&ta, dy, (uint64_t)p.M, (uint64_t)Cout, (uint64_t)ldy, (uint32_t)WG_KROWS) != 0) return -3;
   if (b_tma) {
     if (make_tmap_2d(&tb, src, (uint64_t)p.M, (uint64_t)C, (uint64_t)C, (uint32_t)WG_KROWS) != 0) return -3;
   } else {

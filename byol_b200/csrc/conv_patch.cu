@@ -334,14 +334,15 @@ static int launch_patch(const CUtensorMap& tx, const CUtensorMap& tb, const Patc
                         cudaStream_t stream) {
   constexpr int SMEM = P_PSTAGES * 2 * P_PATCH_SLOT + P_BSTAGES * BN * 128 + 4 * 2048 + 256 + 1024;
   auto kern = conv3x3_patch_kernel<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  const int dev_slot = device_slot();
+  if (!attr_set[dev_slot]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) {
       set_last_error("cudaFuncSetAttribute(conv3x3_patch) failed: %s", cudaGetErrorString(e));
       return -2;
     }
-    attr_set = true;
+    attr_set[dev_slot] = true;
   }
   int grid = sms < p.num_tiles ? sms : p.num_tiles;
   kern<<<grid, 192, SMEM, stream>>>(tx, tb, p);
@@ -568,14 +569,15 @@ static int launch_wpatch(const CUtensorMap& tx, const CUtensorMap& ty, const WPa
                          cudaStream_t stream) {
   constexpr int SMEM = WP_STAGES * (NB * P_PATCH_SLOT + 2 * 16384) + 256 + 1024;
   auto kern = conv3x3_wgrad_patch_kernel<NB>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  const int dev_slot = device_slot();
+  if (!attr_set[dev_slot]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) {
       set_last_error("cudaFuncSetAttribute(conv3x3_wgrad_patch) failed: %s", cudaGetErrorString(e));
       return -2;
     }
-    attr_set = true;
+    attr_set[dev_slot] = true;
   }
   kern<<<grid, 192, SMEM, stream>>>(tx, ty, p);
   return check_launch("conv3x3_wgrad_patch_kernel");

@@ -469,15 +469,7 @@ static PFN_encodeTiledStem stem_encode_fn() {
   return fn;
 }
 
-static int stem_sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
+static int stem_sm_count() { return device_sm_count(); }
 
 // 1 if the stem kernels handle this geometry (otherwise use byol_conv_igemm / byol_conv_wgrad with the NHWC8 input)
 extern "C" int byol_stem4_supported(int Cin, int Cout, int H, int W, int k, int stride, int pad) {
@@ -529,11 +521,12 @@ extern "C" int byol_stem_conv_fprop(const void* xs, const void* ws, void* y, flo
   CUresult r = fn(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_last_error("byol_stem_conv_fprop: tensor map encode failed (%d)", (int)r); return -3; }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  const int dev_slot = device_slot();
+  if (!attr_set[dev_slot]) {
     cudaError_t e = cudaFuncSetAttribute(stem_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_TOTAL);
     if (e != cudaSuccess) { set_last_error("cudaFuncSetAttribute(stem_fprop) failed: %s", cudaGetErrorString(e)); return -2; }
-    attr_set = true;
+    attr_set[dev_slot] = true;
   }
   int grid = 2 * stem_sm_count();
   if (grid > p.num_tiles) grid = p.num_tiles;
@@ -569,11 +562,12 @@ extern "C" int byol_stem_conv_wgrad(const void* xs, const void* dy, float* dw, i
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_last_error("byol_stem_conv_wgrad: tensor map encode failed (%d)", (int)r); return -3; }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  const int dev_slot = device_slot();
+  if (!attr_set[dev_slot]) {
     cudaError_t e = cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_TOTAL);
     if (e != cudaSuccess) { set_last_error("cudaFuncSetAttribute(stem_wgrad) failed: %s", cudaGetErrorString(e)); return -2; }
-    attr_set = true;
+    attr_set[dev_slot] = true;
   }
   int grid = stem_sm_count();
   if (grid > p.num_units) grid = p.num_units;

@@ -400,6 +400,24 @@ extern "C" int byol_subsample2(const void* x, void* y, int N, int H, int W, int 
   return check_launch("subsample2_kernel");
 }
 
+// y[r, c] = bf16(x[r, c]) for c < cols, 0 for cols <= c < ldy (row pitches ldx / ldy in elements)
+__global__ void cast_f32_bf16_2d_kernel(const float* __restrict__ x, bf16* __restrict__ y, int rows, int cols, int ldx,
+                                        int ldy) {
+  const int64_t total = (int64_t)rows * ldy;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ldy);
+    const int64_t r = i / ldy;
+    y[i] = c < cols ? __float2bfloat16_rn(x[r * ldx + c]) : __float2bfloat16_rn(0.f);
+  }
+}
+
+extern "C" int byol_cast_f32_bf16_2d(const float* x, void* y, int rows, int cols, int ldx, int ldy,
+                                     cudaStream_t stream) {
+  BYOL_CHECK_ARG(x && y && rows > 0 && cols > 0 && ldx >= cols && ldy >= cols, "byol_cast_f32_bf16_2d: bad args");
+  cast_f32_bf16_2d_kernel<<<grid_for((int64_t)rows * ldy, 256), 256, 0, stream>>>(x, (bf16*)y, rows, cols, ldx, ldy);
+  return check_launch("cast_f32_bf16_2d_kernel");
+}
+
 extern "C" int byol_cast_f32_bf16(const float* x, void* y, int64_t n, cudaStream_t stream) {
   BYOL_CHECK_ARG(x && y && n > 0, "byol_cast_f32_bf16: bad args");
   cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, (bf16*)y, n);

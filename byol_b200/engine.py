@@ -229,6 +229,17 @@ class Engine(object):
             self.mlps.append((self._unit(l1, bn, "l1"), self._unit(l2, None, "l2")))
         self.cls = self._unit(model.linear_classifier, None, "classifier")
         self.cls.want_dgrad = False
+        # Tensor-core layouts: bf16 activations are moved by TMA (16-byte row pitch), so every layer width on the
+        # path must be a multiple of 8 — except the 3-channel image (padded on conversion) and the classifier's
+        # class count (fp32 logits, pitched gradient), so that any dataset's label space works (main.py:208).
+        for u in self.units:
+            bad_in = u.cin % 8 != 0 and u is not self.stem
+            bad_out = u.cout % 8 != 0 and u is not self.cls
+            if bad_in or bad_out:
+                raise ValueError("byol_b200: layer %s (%s %d -> %d): channel / feature counts on the tensor-core path "
+                                 "must be multiples of 8 (only the image channels and the number of classes are free)"
+                                 % (u.name, u.kind, u.cin, u.cout))
+        self.module_key = self._module_key()
         self.bn_modules = [u.bn for u in self.units if u.bn is not None]
         self.bn_channels = sum(u.cout for u in self.units if u.bn is not None)
         self.sync = any(isinstance(b, nn.SyncBatchNorm) for b in self.bn_modules)
@@ -240,6 +251,14 @@ class Engine(object):
         self.w_online = _Weights(self.units, self.device, True)
         self.w_target = _Weights(self.units, self.device, False)
         self.ready = True
+
+    def _module_key(self):
+        """Identity of every sub-module: module surgery after the first forward (e.g. convert_sync_batchnorm, which
+        re-uses the Parameters but replaces the BatchNorm modules) must rebuild the plan."""
+        return tuple(id(m) for m in self.model.modules())
+
+    def plan_is_current(self):
+        return self.ready and self.is_flat() and self.module_key == self._module_key()
 
     def world(self):
         return comm.world_size()
@@ -657,9 +676,11 @@ class Engine(object):
     def classifier_backward(self, rep_cat_b, d_logits):
         self.notify_backward()
         u = self.cls
-        d = d_logits.contiguous()
+        d = d_logits.contiguous().float()
         ops.col_sum(d, self._gview(u.b_off, u.cout))
-        self._wgrad(u, [rep_cat_b], [ops.cast_bf16(d)])
+        # any class count: the bf16 gradient gets a 16-byte row pitch, the GEMM reads only the first `cout` columns
+        db = ops.cast_bf16(d) if u.cout % 8 == 0 else ops.cast_bf16_pitched(d, (u.cout + 7) // 8 * 8)
+        self._wgrad(u, [rep_cat_b], [db])
         self._join_side_stream()
 
     # ------------------------------------------------------------------------------------------

@@ -12,7 +12,7 @@ from . import ops
 
 __all__ = ['LARS']
 
-_CHUNK = 16384
+_CHUNK = 32768
 
 
 class LARS(Optimizer):
@@ -74,10 +74,11 @@ class LARS(Optimizer):
         total = sum(p.numel() for p, _ in entries)
         use_mom = any(g['momentum'] != 0 for _, g in entries)
         flat_m = torch.zeros(total, dtype=torch.float32, device=dev) if use_mom else None
-        cs, cl, ct, m_ptrs = [], [], [], []
+        cs, cl, ct, first, m_ptrs = [], [], [], [], []
         off = 0
         for t, (p, g) in enumerate(entries):
             n = p.numel()
+            first.append(len(cs))
             for s in range(0, n, _CHUNK):
                 cs.append(s)
                 cl.append(min(_CHUNK, n - s))
@@ -91,14 +92,16 @@ class LARS(Optimizer):
                 st['momentum_buffer'] = view
                 m_ptrs.append(view.data_ptr())
             off += n
+        first.append(len(cs))
         i64 = lambda v: torch.tensor(v, dtype=torch.int64, device=dev)
         i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
         T = len(entries)
         return {
             "p_ptrs": i64([p.data_ptr() for p, _ in entries]), "g_ptrs": i64([p.grad.data_ptr() for p, _ in entries]),
             "m_ptrs": i64(m_ptrs) if use_mom else None, "chunk_start": i64(cs), "chunk_len": i32(cl),
-            "chunk_tensor": i32(ct), "wd": torch.zeros(T, device=dev), "lr": torch.zeros(T, device=dev),
-            "ignore": i32([0] * T), "norms": torch.zeros(2 * T, dtype=torch.float64, device=dev),
+            "chunk_tensor": i32(ct), "tensor_first_chunk": i32(first), "wd": torch.zeros(T, device=dev),
+            "lr": torch.zeros(T, device=dev), "ignore": i32([0] * T),
+            "partial": torch.zeros(2 * len(cs), dtype=torch.float64, device=dev),
             "flat_m": flat_m, "hyper": None, "ptrs": None,
         }
 
@@ -120,6 +123,12 @@ class LARS(Optimizer):
             raise RuntimeError("byol_b200.LARS.step needs CUDA parameters (no CPU path)")
         key = tuple(id(p) for p, _ in entries)
         if self._table is None or self._key != key:
+            for p, _ in entries:
+                # the kernel reads raw fp32 storage: anything else would be silently reinterpreted
+                if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_contiguous() \
+                        or not p.grad.is_contiguous() or p.device != dev or p.grad.device != dev:
+                    raise NotImplementedError("byol_b200.LARS: parameters and gradients must be contiguous fp32 "
+                                              "tensors on one CUDA device (got %s / %s)" % (p.dtype, p.grad.dtype))
             self._table, self._key = self._build(entries, dev), key
         tb = self._table
         ptrs = ([p.data_ptr() for p, _ in entries], [p.grad.data_ptr() for p, _ in entries])

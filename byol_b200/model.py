@@ -133,11 +133,14 @@ class BYOL(nn.Module):
         )
         self.linear_classifier = nn.Linear(base_network_output_size, classifier_output_size)
         self.target_network = CosEMA(total_training_steps, base_decay)
-        # main.py:211-212 runs the EMA once at construction (mean = 0.004 * theta0, step -> 1).
-        # Construction happens on the host; the kernel-side update is deferred to the first use on the GPU.
-        total = sum(p.numel() for p in self.parameters())
-        self.target_network.mean = torch.zeros(total)
-        self._ema_init_pending = True
+        # main.py:211-212 runs the EMA once at construction, on the host: mean = (1 - d0) * theta0 + d0 * 0 with
+        # d0 = decay(step 0) = base_decay, and step -> 1.  Same here (host tensors, fp32), so that
+        # checkpoint restores and params-only loads see exactly the reference's state.
+        with torch.no_grad():
+            theta0 = torch.cat([p.detach().reshape(-1) for p in self.parameters()])
+            d0 = self.target_network.decay_at(0)
+            self.target_network.mean = (1 - d0) * theta0 + d0 * torch.zeros_like(theta0)
+        self.target_network.step = 1
         self._engine = Engine(self)
         self._anchor = None
         self._rep_cat = None
@@ -148,23 +151,11 @@ class BYOL(nn.Module):
         self._engine.ready = False
         return out
 
-    def load_state_dict(self, state_dict, *args, **kwargs):
-        out = super(BYOL, self).load_state_dict(state_dict, *args, **kwargs)
-        if "target_network.mean" in state_dict:
-            self._ema_init_pending = False    # a restored target network supersedes the construction-time init
-        return out
-
     def _ensure_ready(self, batch):
         eng = self._engine
-        if not eng.ready or not eng.is_flat():
+        if not eng.plan_is_current():
             eng.flatten()
             eng.build_plan()
-        if self._ema_init_pending:
-            was = self.target_network.training
-            self.target_network.train()
-            self.target_network(eng.theta)
-            self.target_network.train(was)
-            self._ema_init_pending = False
         if self._anchor is None or self._anchor.device != eng.device:
             self._anchor = torch.zeros(1, device=eng.device, requires_grad=True)
         if self._rep_cat is None or self._rep_cat.shape[0] != 2 * batch or self._rep_cat.device != eng.device:

@@ -42,3 +42,32 @@ def loss_function(online_prediction1, online_prediction2, target_projection1, ta
     if not online_prediction1.is_cuda:
         raise RuntimeError("byol_b200.objective.loss_function needs CUDA tensors (no CPU path)")
     return _ByolLossFn.apply(online_prediction1, online_prediction2, target_projection1, target_projection2)
+
+
+class _CrossEntropyTopkFn(torch.autograd.Function):
+    """Softmax cross-entropy + top-1 / top-5 accuracy of the linear probe in ONE launch
+    (/root/reference/main.py:596-598: F.cross_entropy(linear_preds, labels) and helpers.metrics.topk)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        lg = logits if (logits.dtype == torch.float32 and logits.stride(-1) == 1) else logits.contiguous().float()
+        lab = labels.contiguous()
+        out, row_lse = ops.ce_topk_fwd(lg, lab)
+        ctx.save_for_backward(lg, lab, row_lse)
+        ctx.mark_non_differentiable(out[1:2], out[2:3])
+        return out[0].clone().view(()), out[1:2], out[2:3]
+
+    @staticmethod
+    def backward(ctx, grad_loss, _g1, _g5):
+        lg, lab, row_lse = ctx.saved_tensors
+        go = grad_loss.contiguous().float().view(1)
+        return ops.ce_bwd(lg, lab, row_lse, go), None
+
+
+def cross_entropy_topk(logits, labels):
+    """(mean cross-entropy loss [differentiable w.r.t. logits], top-1 %, top-5 %) — the reference computes these with
+    F.cross_entropy + metrics.topk(output, target, topk=(1, 5)) (main.py:596-598); accuracies are 1-element
+    tensors like the reference's."""
+    if not logits.is_cuda:
+        raise RuntimeError("byol_b200.objective.cross_entropy_topk needs CUDA tensors (no CPU path)")
+    return _CrossEntropyTopkFn.apply(logits, labels)

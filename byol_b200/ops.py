@@ -139,6 +139,17 @@ def prep_weights_multi(flat, pool_f, pool_d, desc):
           "byol_prep_weights_multi")
 
 
+def cast_bf16_pitched(x2d, ldy):
+    """fp32 [rows, cols] (any row stride) -> bf16 [rows, ldy] with zero padding columns (ldy >= cols)."""
+    if x2d.dtype != F32 or not x2d.is_cuda or x2d.stride(1) != 1:
+        raise ValueError("cast_bf16_pitched: need a CUDA fp32 matrix with unit column stride")
+    rows, cols = x2d.shape
+    out = torch.empty((rows, ldy), dtype=BF16, device=x2d.device)
+    check(lib.byol_cast_f32_bf16_2d(_ptr(x2d), _ptr(out), rows, cols, x2d.stride(0), ldy, _stream()),
+          "byol_cast_f32_bf16_2d")
+    return out
+
+
 def cast_bf16(x, out=None):
     _chk(x, F32, "x")
     if out is None:
@@ -185,13 +196,14 @@ def conv_dgrad(dy, w_d, h, w, kh, kw, stride, pad, resid=None, out=None, force_g
 
 
 def conv_wgrad(x, dy, dw, kh, kw, stride, pad, force_gather=False):
-    """dw[Cout,Cin,KH,KW] (fp32, reference layout) += dy^T * im2col(x).  x: [N,H,W,Cpad], dy: [N,Ho,Wo,Cout]."""
+    """dw[Cout,Cin,KH,KW] (fp32, reference layout) += dy^T * im2col(x).  x: [N,H,W,Cpad], dy: [N,Ho,Wo,ldy] whose
+    first Cout = dw.shape[0] columns are the gradient (ldy > Cout: pitched rows, e.g. a 10-class classifier)."""
     _chk(x, BF16, "x"); _chk(dy, BF16, "dy"); _chk(dw, F32, "dw")
     n, h, w, c = x.shape
-    _, ho, wo, cout = dy.shape
-    cin_real = dw.shape[1]
-    check(lib.byol_conv_wgrad(_ptr(x), _ptr(dy), _ptr(dw), n, h, w, c, cin_real, ho, wo, cout, kh, kw, stride, pad,
-                              int(force_gather), _stream()), "byol_conv_wgrad")
+    _, ho, wo, ldy = dy.shape
+    cout, cin_real = dw.shape[0], dw.shape[1]
+    check(lib.byol_conv_wgrad(_ptr(x), _ptr(dy), _ptr(dw), n, h, w, c, cin_real, ho, wo, cout, ldy, kh, kw, stride,
+                              pad, int(force_gather), _stream()), "byol_conv_wgrad")
     return dw
 
 
@@ -228,11 +240,8 @@ def bn_stats(x2d, stats):
 
 
 def bn_finalize(stats, count, gamma, beta, running_mean, running_var, momentum, eps, coeffs):
-    """coeffs: fp32 [4, C] receiving scale, shift, mean, invstd.  running_* updated in place (may be None)."""
-    c = gamma.numel()
-    check(lib.byol_bn_finalize(_ptr(stats), float(count), _ptr(gamma), _ptr(beta), _ptr(running_mean),
-                               _ptr(running_var), float(momentum), float(eps), _ptr(coeffs[0]), _ptr(coeffs[1]),
-                               _ptr(coeffs[2]), _ptr(coeffs[3]), c, _stream()), "byol_bn_finalize")
+    """Single-lane form of :func:`bn_finalize_lanes`; coeffs: fp32 [4, C] receiving scale, shift, mean, invstd."""
+    bn_finalize_lanes(stats, count, [gamma], [beta], running_mean, running_var, momentum, eps, coeffs)
     return coeffs
 
 
@@ -380,10 +389,38 @@ def ema_update(x, mean, one_minus_decay, decay):
 
 def lars_sgd_step(table, trust_coef, eps, momentum, first_step):
     """table: dict of device tensors p_ptrs/g_ptrs/m_ptrs (int64 pointer tables, m_ptrs may be None),
-    chunk_start (int64), chunk_len / chunk_tensor (int32), wd / lr (fp32), ignore (int32), norms (fp64 [2*T])."""
+    chunk_start (int64), chunk_len / chunk_tensor / tensor_first_chunk (int32), wd / lr (fp32), ignore (int32),
+    partial (fp64 [2 * chunks])."""
     check(lib.byol_lars_sgd_step(_ptr(table["p_ptrs"]), _ptr(table["g_ptrs"]), _ptr(table.get("m_ptrs")),
                                  _ptr(table["chunk_start"]), _ptr(table["chunk_len"]), _ptr(table["chunk_tensor"]),
-                                 table["chunk_start"].numel(), _ptr(table["wd"]), _ptr(table["lr"]),
-                                 _ptr(table["ignore"]), table["wd"].numel(), _ptr(table["norms"]),
-                                 float(trust_coef), float(eps), float(momentum), int(first_step), _stream()),
+                                 table["chunk_start"].numel(), _ptr(table["tensor_first_chunk"]), _ptr(table["wd"]),
+                                 _ptr(table["lr"]), _ptr(table["ignore"]), table["wd"].numel(),
+                                 _ptr(table["partial"]), float(trust_coef), float(eps), float(momentum),
+                                 int(first_step), _stream()),
           "byol_lars_sgd_step", kernels=2)
+
+
+def ce_topk_fwd(logits, labels, scratch=None):
+    """Softmax cross-entropy (mean) + top-1 / top-5 accuracy (%) of fp32 logits [R, C] in one launch; `labels` has R
+    entries or a divisor of R (row r uses labels[r % len]: both views of a sample share its label).
+    Returns (out fp32 [3] = loss, top1, top5; row_lse fp32 [R] for the backward pass)."""
+    _chk(logits, F32, "logits")
+    if labels.dtype != torch.int64 or not labels.is_cuda or not labels.is_contiguous():
+        raise ValueError("labels must be a contiguous CUDA int64 tensor")
+    r, c = logits.shape
+    if labels.numel() == 0 or r % labels.numel() != 0:
+        raise ValueError("labels: %d entries do not tile %d rows" % (labels.numel(), r))
+    dev = logits.device
+    fl = torch.empty(2 * r + 3, dtype=F32, device=dev)            # row_lse | row_loss | out
+    it = torch.zeros(r + 1, dtype=torch.int32, device=dev)        # row_rank | ticket (must start at 0)
+    check(lib.byol_ce_topk_fwd(_ptr(logits), _ptr(labels), labels.numel(), r, c, logits.stride(0), _ptr(fl), _ptr(fl[r:]), _ptr(it),
+                               _ptr(it[r:]), _ptr(fl[2 * r:]), _stream()), "byol_ce_topk_fwd")
+    return fl[2 * r:], fl[:r]
+
+
+def ce_bwd(logits, labels, row_lse, grad_out):
+    r, c = logits.shape
+    d = torch.empty((r, c), dtype=F32, device=logits.device)
+    check(lib.byol_ce_bwd(_ptr(logits), _ptr(labels), labels.numel(), _ptr(row_lse), _ptr(grad_out), r, c, logits.stride(0), _ptr(d), c,
+                          _stream()), "byol_ce_bwd")
+    return d

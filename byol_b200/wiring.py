@@ -11,10 +11,9 @@ into the reference's training script.
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .lars import LARS  # noqa: F401 (re-exported)
-from .objective import loss_function
+from .objective import cross_entropy_topk, loss_function
 
 
 def add_weight_decay(model, weight_decay=1e-5, skip_list=()):
@@ -64,11 +63,16 @@ class DistributedDataParallelPassthrough(nn.Module):
 
 
 def topk(output, target, topk=(1,)):
+    """helpers.metrics.topk (main.py:598) for k in {1, 5}: percentage of rows whose label is among the k largest
+    logits, from the fused kernel (rank of the label's logit = number of strictly larger logits)."""
+    from . import ops
+    if any(k not in (1, 5) for k in topk):
+        raise NotImplementedError("byol_b200.wiring.topk: k must be 1 or 5")
     with torch.no_grad():
-        maxk = max(topk)
-        _, pred = output.topk(maxk, 1, True, True)
-        correct = pred.t().eq(target.view(1, -1))
-        return [correct[:k].reshape(-1).float().sum(0, keepdim=True).mul_(100.0 / target.size(0)) for k in topk]
+        lg = output.detach()
+        lg = lg if (lg.dtype == torch.float32 and lg.stride(-1) == 1) else lg.contiguous().float()
+        out, _ = ops.ce_topk_fwd(lg, target.contiguous())
+        return [out[1:2] if k == 1 else out[2:3] for k in topk]
 
 
 def train_step(model, optimizer, augmentation1, augmentation2, labels):
@@ -78,9 +82,9 @@ def train_step(model, optimizer, augmentation1, augmentation2, labels):
                               online_prediction2=output_dict['online_prediction2'],
                               target_projection1=output_dict['target_projection1'],
                               target_projection2=output_dict['target_projection2'])
-    classifier_labels = torch.cat([labels, labels], 0)
-    classifier_loss = F.cross_entropy(input=output_dict['linear_preds'], target=classifier_labels)
-    acc1, acc5 = topk(output_dict['linear_preds'], classifier_labels, topk=(1, 5))
+    # F.cross_entropy + metrics.topk on cat([labels, labels]) (main.py:591,596-598) in one kernel: row r of the
+    # [2b, classes] logits uses labels[r % b], so the concatenated label vector is never materialised
+    classifier_loss, acc1, acc5 = cross_entropy_topk(output_dict['linear_preds'], labels)
     loss = byol_loss + classifier_loss
     optimizer.zero_grad()
     loss.backward()

@@ -49,8 +49,8 @@ int byol_conv_igemm(const void* src, const void* wt, void* dst, const void* resi
 /* dW[Cout][Cin_real][KH][KW] (fp32, accumulated) += dY^T x im2col(x): replaces cuDNN wgrad / cuBLAS in the
  * autograd of main.py:617 (loss.backward()). */
 int byol_conv_wgrad(const void* src, const void* dy, float* dw, int Nimg, int Hs, int Ws, int C, int Cin_real,
-                    int Ho, int Wo, int Cout, int KH, int KW, int stride, int pad, int force_gather,
-                    byol_stream_t stream);
+                    int Ho, int Wo, int Cout, int ldy /* row pitch of dy, 0 = Cout */, int KH, int KW, int stride,
+                    int pad, int force_gather, byol_stream_t stream);
 
 /* ---- stem (7x7 / stride 2 / pad 3, <= 4 input channels, 64 output channels, W <= 256): the torchvision ResNet
  *      conv1 reached from main.py:237.  The image is converted once to zero-padded NHWC4 bf16
@@ -70,10 +70,7 @@ int byol_stem_conv_wgrad(const void* xs, const void* dy, float* dw, int N, int C
 /* ---- BatchNorm (train / eval, optionally cross-rank): replaces ATen batch_norm and SyncBatchNorm
  *      (main.py:196,202,237,433; torch/nn/modules/_functions.py:10-205) ---- */
 int byol_bn_stats(const void* x, float* stats /* zeroed [2C] */, int M, int C, byol_stream_t stream);
-int byol_bn_finalize(const float* stats, double count, const float* gamma, const float* beta, float* running_mean,
-                     float* running_var, float momentum, float eps, float* scale, float* shift, float* mean,
-                     float* invstd, int C, byol_stream_t stream);
-/* same for L <= 4 lock-step lanes in one launch: stats [L][2C], coeffs [L][4][C] = scale, shift, mean, invstd;
+/* statistics -> coefficients for L <= 4 lock-step lanes in one launch: stats [L][2C], coeffs [L][4][C] = scale, shift, mean, invstd;
  * running statistics are updated lane after lane (the order of the reference's four forward passes) */
 int byol_bn_finalize_lanes(const float* stats, double count, int L, const float* gamma0, const float* beta0,
                            const float* gamma1, const float* beta1, const float* gamma2, const float* beta2,
@@ -111,6 +108,8 @@ int byol_prep_weights_multi(const float* flat, void* pool_f, void* pool_d, const
 /* y[n,i,j,:] = x[n,2i,2j,:] (input of a 1x1 / stride-2 downsample conv, compacted for the TMA-fed GEMM) */
 int byol_subsample2(const void* x, void* y, int N, int H, int W, int C, byol_stream_t stream);
 int byol_cast_f32_bf16(const float* x, void* y, int64_t n, byol_stream_t stream);
+/* y[r, c] = bf16(x[r, c]) for c < cols and 0 for cols <= c < ldy (pitched copy, e.g. classifier gradients) */
+int byol_cast_f32_bf16_2d(const float* x, void* y, int rows, int cols, int ldx, int ldy, byol_stream_t stream);
 int byol_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, int k, int s, int p,
                      byol_stream_t stream);
 /* stem fusion: y = maxpool(relu(x*scale + shift)); values and argmax indices equal bn_apply + maxpool_fwd exactly */
@@ -134,11 +133,23 @@ int byol_ema_update(const float* x, float* mean, float one_minus_decay, float de
 
 /* ---- optimizer: replaces LARS.apply_adaptive_lrs + SGD(momentum).step, optimizers/lars.py:84-127 ----
  * p_ptrs / g_ptrs / m_ptrs: device arrays of num_tensors fp32 pointers (m_ptrs may be NULL: no momentum);
- * chunk tables split the tensors into <= 16384-element work items; norms: 2*num_tensors doubles (scratch). */
+ * chunk tables split the tensors into work items (chunks of one tensor are contiguous:
+ * [tensor_first_chunk[t], tensor_first_chunk[t+1])); partial: 2*num_chunks doubles of scratch.  No atomics: the
+ * per-tensor norms are bit-reproducible, so data-parallel replicas stay bit-identical (main.py:440). */
 int byol_lars_sgd_step(const void* p_ptrs, const void* g_ptrs, const void* m_ptrs, const int64_t* chunk_start,
-                       const int* chunk_len, const int* chunk_tensor, int num_chunks, const float* wd,
-                       const float* lr, const int* ignore, int num_tensors, double* norms, float trust_coef,
-                       float eps, float momentum, int first_step, byol_stream_t stream);
+                       const int* chunk_len, const int* chunk_tensor, int num_chunks, const int* tensor_first_chunk,
+                       const float* wd, const float* lr, const int* ignore, int num_tensors, double* partial,
+                       float trust_coef, float eps, float momentum, int first_step, byol_stream_t stream);
+
+/* ---- linear-probe objective: replaces F.cross_entropy + helpers.metrics.topk, main.py:596-598 ----
+ * logits fp32 [R, C] (row pitch ld), labels int64 [label_rows] (row r uses labels[r % label_rows]: the two views
+ * of a sample share its label, main.py:591); scratch: row_lse / row_loss [R] floats, row_rank [R] ints,
+ * ticket: one zeroed uint32.  out = [mean loss, top-1 %, top-5 %] (deterministic row-order reduction). */
+int byol_ce_topk_fwd(const float* logits, const int64_t* labels, int label_rows, int R, int C, int ld, float* row_lse,
+                     float* row_loss, int* row_rank, unsigned int* ticket, float* out, byol_stream_t stream);
+/* dlogits[r, c] = grad_out / R * (softmax(logits[r])[c] - [c == labels[r]]) */
+int byol_ce_bwd(const float* logits, const int64_t* labels, int label_rows, const float* row_lse, const float* grad_out, int R, int C,
+                int ld, float* dlogits, int ldd, byol_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(raw, name), "libbyol_b200.so does not export %s" % name
     # and the Python binding table covers exactly the header
     assert sorted(_lib.EXPORTED_SYMBOLS) == syms
-    assert _lib.lib.byol_abi_version() == 1
+    assert _lib.lib.byol_abi_version() == 2
     assert _lib.last_error() == ""
 
 

@@ -253,13 +253,15 @@ def test_lars_sgd(cuda):
     flat_g = torch.cat([x.reshape(-1) for x in grads]).to(cuda)
     flat_m = torch.zeros_like(flat_p)
     CH = 4096
-    cs, cl, ct = [], [], []
+    cs, cl, ct, first = [], [], [], []
     off = 0
     for t, p in enumerate(params):
         nel = p.numel()
+        first.append(len(cs))
         for s in range(0, nel, CH):
             cs.append(s); cl.append(min(CH, nel - s)); ct.append(t)
         off += nel
+    first.append(len(cs))
     offs = [0]
     for p in params:
         offs.append(offs[-1] + p.numel())
@@ -273,7 +275,8 @@ def test_lars_sgd(cuda):
         "wd": torch.tensor([0.0 if i else wd for i in ignore], device=cuda),
         "lr": torch.full((len(shapes),), lr, device=cuda),
         "ignore": torch.tensor(ignore, dtype=torch.int32, device=cuda),
-        "norms": torch.zeros(2 * len(shapes), dtype=torch.float64, device=cuda),
+        "tensor_first_chunk": torch.tensor(first, dtype=torch.int32, device=cuda),
+        "partial": torch.zeros(2 * len(cs), dtype=torch.float64, device=cuda),
     }
     # reference: /root/reference/optimizers/lars.py:84-127 around torch.optim.SGD(momentum=0.9)
     ref_p = [p.clone() for p in params]
@@ -294,3 +297,77 @@ def test_lars_sgd(cuda):
     torch.cuda.synchronize()
     assert_close("lars_params", flat_p, torch.cat([p.reshape(-1) for p in ref_p]), atol=1e-7, rtol=1e-5)
     assert_close("lars_momentum", flat_m, torch.cat([m.reshape(-1) for m in ref_m]), atol=1e-9, rtol=1e-5)
+
+
+def test_lars_sgd_is_deterministic_and_handles_unaligned_tensors(cuda):
+    """Replicas must stay bit-identical under data parallelism (main.py:440): the per-tensor norms are reduced in a
+    fixed order (no atomics), so two executions on the same inputs give bit-identical parameters.  Tensors whose
+    storage is not 16-byte aligned take the scalar path and must give the same values as the vector path."""
+    from byol_b200.lars import LARS
+    g = torch.Generator().manual_seed(19)
+    shapes = [(257, 129), (3,), (1000, 50), (77,), (300001,)]
+    runs = []
+    for offset in (0, 0, 1):          # third run: every tensor starts one float off a 16-byte boundary
+        torch.manual_seed(0)
+        ps, gs = [], []
+        g = torch.Generator().manual_seed(19)
+        for sh in shapes:
+            n = int(np.prod(sh))
+            base = torch.zeros(n + 4, device=cuda)
+            gbase = torch.zeros(n + 4, device=cuda)
+            p = torch.nn.Parameter(base[offset:offset + n].view(sh))
+            with torch.no_grad():
+                p.copy_(torch.randn(sh, generator=g) * 0.1)
+            p.grad = gbase[offset:offset + n].view(sh)
+            p.grad.copy_(torch.randn(sh, generator=g) * 0.01)
+            ps.append(p); gs.append(p.grad)
+        groups = [{"params": [ps[1], ps[3]], "weight_decay": 0.0, "ignore": True},
+                  {"params": [ps[0], ps[2], ps[4]], "weight_decay": 1e-6, "ignore": False}]
+        opt = LARS(torch.optim.SGD(groups, lr=0.3, momentum=0.9), eps=0.0)
+        for _ in range(3):
+            opt.step()
+        torch.cuda.synchronize()
+        runs.append(torch.cat([p.detach().reshape(-1).cpu() for p in ps]))
+    assert torch.equal(runs[0], runs[1]), "LARS step is not run-to-run deterministic"
+    assert torch.allclose(runs[0], runs[2], rtol=1e-6, atol=1e-8)
+
+
+def test_lars_rejects_non_fp32(cuda):
+    from byol_b200.lars import LARS
+    p = torch.nn.Parameter(torch.randn(8, 8, device=cuda, dtype=torch.float16))
+    p.grad = torch.randn_like(p)
+    opt = LARS(torch.optim.SGD([{"params": [p], "weight_decay": 0.0, "ignore": False}], lr=0.1, momentum=0.9))
+    with pytest.raises(NotImplementedError):
+        opt.step()
+
+
+@pytest.mark.parametrize("rows,classes,tile", [(16, 1000, 1), (1024, 1000, 2), (24, 10, 2), (7, 37, 1)])
+def test_cross_entropy_topk(cuda, rows, classes, tile):
+    """main.py:596-598: F.cross_entropy + metrics.topk((1, 5)) on the classifier logits, here one kernel (+ its
+    backward); `tile` = 2 checks the implicit cat([labels, labels])."""
+    from byol_b200.objective import cross_entropy_topk
+    from byol_b200 import wiring
+    g = torch.Generator().manual_seed(23)
+    logits = torch.randn(rows, classes, generator=g) * 3
+    labels = torch.randint(0, classes, (rows // tile,), generator=g)
+    full = torch.cat([labels] * tile)
+    logits[0, full[0]] = logits[0].max() + 1.0          # one certain top-1 hit
+    lr = logits.clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lr, full)
+    (ref * 0.37).backward()
+    _, pred = logits.topk(min(5, classes), 1, True, True)
+    correct = pred.t().eq(full.view(1, -1))
+    ref1 = correct[:1].reshape(-1).float().sum() * 100.0 / rows
+    ref5 = correct[:5].reshape(-1).float().sum() * 100.0 / rows
+    ld = logits.to(cuda).requires_grad_(True)
+    loss, a1, a5 = cross_entropy_topk(ld, labels.to(cuda))
+    (loss * 0.37).backward()
+    torch.cuda.synchronize()
+    assert_close("ce_loss", loss.detach().reshape(1), ref.detach().reshape(1), atol=1e-6, rtol=1e-5)
+    assert_close("ce_dlogits", ld.grad, lr.grad, atol=1e-8, rtol=1e-4)
+    assert abs(float(a1) - float(ref1)) < 1e-4 and abs(float(a5) - float(ref5)) < 1e-4
+    t1, t5 = wiring.topk(logits.to(cuda), full.to(cuda), topk=(1, 5))
+    assert abs(float(t1) - float(ref1)) < 1e-4 and abs(float(t5) - float(ref5)) < 1e-4
+    # deterministic: the row reduction has a fixed order
+    loss2, _, _ = cross_entropy_topk(ld.detach(), labels.to(cuda))
+    assert torch.equal(loss2, loss.detach())

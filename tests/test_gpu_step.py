@@ -186,3 +186,57 @@ def test_eval_forward(cuda):
         e = _rel(out[key], ref[key])
         print(key, e)
         assert e < 4e-2, key
+
+
+def test_small_label_space_classifier(cuda):
+    """main.py:208 builds nn.Linear(representation, loader.output_size) for ANY class count (e.g. a 10-class image
+    folder): the classifier's fp32 logits / pitched bf16 gradient must not need a multiple of 8."""
+    import torch.nn.functional as F
+    from byol_b200.model import BYOL
+    from byol_b200 import wiring
+    torch.manual_seed(5)
+    arch, classes, b = "resnet:basic:1,1,1,1", 10, 8
+    model = BYOL(512, 256, classes, 10, arch=arch).cuda().train()
+    opt = wiring.build_optimizer(model, global_batch_size=256)
+    g = torch.Generator().manual_seed(6)
+    a1, a2 = torch.rand(b, 3, 64, 64, generator=g).cuda(), torch.rand(b, 3, 64, 64, generator=g).cuda()
+    lab = torch.randint(0, classes, (b,), generator=g).cuda()
+    out = model(a1, a2)
+    assert out["linear_preds"].shape == (2 * b, classes)
+    # logits and classifier gradients against plain fp32 torch on the (bf16-rounded) operands the kernel sees
+    rep = torch.cat([out["online_representation1"], out["online_representation2"]]).detach()
+    W, bias = model.linear_classifier.weight.detach().clone(), model.linear_classifier.bias.detach().clone()
+    rb = rep.to(torch.bfloat16).float()
+    ref_logits = rb @ W.to(torch.bfloat16).float().t() + bias
+    assert torch.allclose(out["linear_preds"], ref_logits, rtol=2e-2, atol=2e-2)
+    loss = F.cross_entropy(out["linear_preds"], torch.cat([lab, lab]))
+    opt.zero_grad()
+    loss.backward()
+    torch.cuda.synchronize()
+    lg = out["linear_preds"].detach().clone().requires_grad_(True)
+    F.cross_entropy(lg, torch.cat([lab, lab])).backward()
+    ref_dw = lg.grad.to(torch.bfloat16).float().t() @ rb
+    got = model.linear_classifier.weight.grad
+    cos = float((got.flatten() @ ref_dw.flatten()) / (got.norm() * ref_dw.norm()))
+    assert cos > 0.999, cos
+    assert torch.allclose(model.linear_classifier.bias.grad, lg.grad.sum(0), rtol=1e-4, atol=1e-6)
+    stats = wiring.train_step(model, opt, a1, a2, lab)        # the fused CE/top-k path with the implicit label tiling
+    assert torch.isfinite(stats["loss_mean"]) and 0.0 <= float(stats["top5_mean"]) <= 100.0
+
+
+def test_module_surgery_after_first_forward_rebuilds_plan(cuda):
+    """nn.SyncBatchNorm.convert_sync_batchnorm after the first forward re-uses the Parameters but replaces the BN
+    modules: the engine must follow (running statistics of the NEW modules are the ones updated)."""
+    import torch.nn as nn
+    from byol_b200.model import BYOL
+    torch.manual_seed(5)
+    model = BYOL(512, 256, 1000, 10, arch="resnet:basic:1,1,1,1").cuda().train()
+    x = torch.rand(4, 3, 64, 64, device=cuda)
+    with torch.no_grad():
+        model(x, x)
+    model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
+    before = model.base_network[1].num_batches_tracked.clone()
+    with torch.no_grad():
+        model(x, x)
+    assert isinstance(model.base_network[1], nn.SyncBatchNorm)
+    assert int(model.base_network[1].num_batches_tracked) == int(before) + 4
