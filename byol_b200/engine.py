@@ -17,6 +17,8 @@ Reference semantics reproduced (file:line are /root/reference):
 Data layout: activations NHWC bf16; conv outputs are stored raw ("y") and normalised copies ("a") are
 materialised by a fused BN-apply(+residual)+ReLU kernel; BN statistics come from the conv epilogue.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -98,6 +100,12 @@ class _Pool(object):
         return t
 
 
+class _GraphedStep(object):
+    """One captured training step: fixed buffers + the forward / backward CUDA graphs (see Engine.graphed_step)."""
+    __slots__ = ("inputs", "saved", "outs", "logits", "d_pred", "fwd", "bwd", "pool", "fwd_launches", "bwd_launches",
+                 "mean_ptr", "pending")
+
+
 class Engine(object):
     def __init__(self, model):
         self.model = model
@@ -113,6 +121,9 @@ class Engine(object):
         self._bwd_streams = None
         self._fin_events = None
         self._group_order = 0
+        # BYOL_B200_GRAPHS=0 keeps every launch eager (debugging / profiling single kernels)
+        self.use_graphs = os.environ.get("BYOL_B200_GRAPHS", "1") != "0"
+        self.graphs = {}
 
     # ------------------------------------------------------------------------------------------
     # flat buffers
@@ -250,6 +261,7 @@ class Engine(object):
         self._bwd_streams = self._fwd_streams
         self.w_online = _Weights(self.units, self.device, True)
         self.w_target = _Weights(self.units, self.device, False)
+        self.graphs = {}           # captured steps point into the old buffers
         self.ready = True
 
     def _module_key(self):
@@ -376,7 +388,24 @@ class Engine(object):
                 saved[key] = {"x": xs[i], "h": h[i], "c": c[i], "a": a[i]}
         return outs_f, outs_b
 
-    def forward_lanes(self, augs, lanes, train, rep_bf16_out=None):
+    def convert_inputs(self, augs, outs=None):
+        """fp32 NCHW images -> the stem's input layout, once per distinct tensor (the online and the target lane of a
+        view share it).  Returns per lane (nhwc8 | None, stem4 | None, H, W); `outs` (a previous result) is
+        overwritten in place (CUDA-graph replays read these fixed buffers)."""
+        st = self.stem
+        conv, res = {}, []
+        for i, a in enumerate(augs):
+            if id(a) not in conv:
+                # padded NHWC4 for the dedicated stem kernels, NHWC8 for the generic path (e.g. 384x384 images)
+                use4 = self.w_online.stem4_ok and ops.stem4_supported(st.cin, st.cout, a.shape[2], a.shape[3], st.k,
+                                                                      st.stride, st.pad)
+                o = outs[i] if outs is not None else (None, None)
+                conv[id(a)] = (None, ops.nchw_to_stem4(a, out=o[1]), a.shape[2], a.shape[3]) if use4 else \
+                    (ops.nchw_to_nhwc8(a, out=o[0]), None, a.shape[2], a.shape[3])
+            res.append(conv[id(a)])
+        return res
+
+    def forward_lanes(self, augs, lanes, train, rep_bf16_out=None, x8=None):
         """augs: fp32 NCHW inputs per lane; lanes: (flat params, weight set, saved dict or None) per lane.
         Returns per lane (representation fp32, projection fp32, prediction fp32).
 
@@ -386,17 +415,8 @@ class Engine(object):
         through one event per layer."""
         L = len(lanes)
         main = torch.cuda.current_stream()
-        conv = {}
-        x8 = []
-        st = self.stem
-        for a in augs:     # online and target lanes of one view share the converted input
-            if id(a) not in conv:
-                # padded NHWC4 for the dedicated stem kernels, NHWC8 for the generic path (e.g. 384x384 images)
-                use4 = lanes[0][1].stem4_ok and ops.stem4_supported(st.cin, st.cout, a.shape[2], a.shape[3], st.k,
-                                                                    st.stride, st.pad)
-                conv[id(a)] = (None, ops.nchw_to_stem4(a), a.shape[2], a.shape[3]) if use4 else \
-                    (ops.nchw_to_nhwc8(a), None, a.shape[2], a.shape[3])
-            x8.append(conv[id(a)])
+        if x8 is None:
+            x8 = self.convert_inputs(augs)
         if rep_bf16_out is None:
             rep_bf16_out = [None] * L
         # under SyncBatchNorm the per-layer all-reduces serialise the lane pairs anyway: run all four lanes lock-step
@@ -605,11 +625,12 @@ class Engine(object):
         self._wgrad(l1, [s["x"] for s in S], dhs)
         return [ops.linear_dgrad(dhs[i], self.w_online.wd[l1.idx]) for i in range(L)]
 
-    def backward_online(self, saved, d_reps, d_projs, d_preds):
+    def backward_online(self, saved, d_reps, d_projs, d_preds, notify=True):
         """Backward of the online views.  Each view runs on its own CUDA stream (forked from / joined into the
         caller's stream) so that one view's HBM-bound BatchNorm-backward kernels overlap the other's GEMMs; both
         accumulate into the same flat gradient buffer with atomic reductions."""
-        self.notify_backward()
+        if notify:
+            self.notify_backward()
         L = len(saved)
         main = torch.cuda.current_stream()
         if not (self.multi_stream and L == 2) or (self.sync and self.world() > 1):
@@ -666,6 +687,68 @@ class Engine(object):
         dy0, _ = self._bn_bwd(self.stem, g0, [s["y0"] for s in saved], [s["c0"] for s in saved], 1)
         self._wgrad(self.stem, [s["x8"] for s in saved], dy0)
         self._join_side_stream()
+
+    # ------------------------------------------------------------------------------------------
+    # CUDA-graph replay of the training step (forward of the 4 lanes + classifier, backward of the 2 online views)
+    # ------------------------------------------------------------------------------------------
+    def graph_key(self, a1):
+        return (tuple(a1.shape), self.world(), bool(self.sync), self.theta.data_ptr(), self.multi_stream,
+                self.overlap_wgrad)
+
+    def graphed_step(self, model, a1, a2):
+        """Returns the captured step for this input geometry, or None while it is still warming up / if graphs are
+        disabled.  First call with a new geometry: eager (sets kernel attributes, sizes the allocator).  Second call:
+        capture — all ~1000 launches of the forward pass go into one graph and those of the backward pass into a
+        second one, both in one private memory pool; the activations saved for the backward pass, the inputs, the
+        outputs and the incoming prediction gradients are fixed buffers.  From then on a step costs two graph
+        launches plus a handful of small eager kernels (input layout, loss, EMA, LARS) on the host."""
+        if not self.use_graphs:
+            return None
+        key = self.graph_key(a1)
+        st = self.graphs.get(key)
+        if st is None:
+            self.graphs = {key: "warm"}      # one geometry at a time: a captured step pins its activations
+            return None
+        if st == "warm":
+            st = self._capture_step(model, a1, a2)
+            self.graphs[key] = st
+        return st
+
+    def _capture_step(self, model, a1, a2):
+        from ._lib import launch_count
+        st = _GraphedStep()
+        st.pending = False
+        b = a1.shape[0]
+        # fixed input buffers (written by the eager layout kernels before every replay)
+        st.inputs = self.convert_inputs([a1]) + self.convert_inputs([a2])
+        st.saved = [{}, {}]
+        mean = model.target_network.mean
+        lanes = [(self.theta, self.w_online, st.saved[0]), (self.theta, self.w_online, st.saved[1]),
+                 (mean, self.w_target, None), (mean, self.w_target, None)]
+        st.mean_ptr = mean.data_ptr()
+        rep_cat = model._rep_cat
+        torch.cuda.synchronize()
+        pool = torch.cuda.graph_pool_handle()
+        st.fwd = torch.cuda.CUDAGraph()
+        n0 = launch_count[0]
+        with torch.cuda.graph(st.fwd, pool=pool, capture_error_mode="thread_local"):
+            self.prep_weights(self.theta, self.w_online, want_dgrad=True)
+            self.prep_weights(mean, self.w_target, want_dgrad=False)
+            outs, _ = self.forward_lanes(None, lanes, True, rep_bf16_out=[rep_cat[:b], rep_cat[b:], None, None],
+                                         x8=[st.inputs[0], st.inputs[1], st.inputs[0], st.inputs[1]])
+            st.logits = self.classifier_forward(rep_cat)
+        st.fwd_launches = launch_count[0] - n0
+        st.outs = [t for o in outs for t in o]
+        # backward for the usual gradient pattern: only the two online predictions receive a gradient
+        # (objective.py:23-24 detaches the targets; main.py:601 adds the classifier loss, which is stop-grad)
+        st.d_pred = [torch.zeros_like(st.outs[2]), torch.zeros_like(st.outs[5])]
+        st.bwd = torch.cuda.CUDAGraph()
+        n0 = launch_count[0]
+        with torch.cuda.graph(st.bwd, pool=pool, capture_error_mode="thread_local"):
+            self.backward_online(st.saved, [None, None], [None, None], st.d_pred, notify=False)
+        st.bwd_launches = launch_count[0] - n0
+        st.pool = pool
+        return st
 
     # classifier (stop-grad input; main.py:250-252)
     def classifier_forward(self, rep_cat_b):

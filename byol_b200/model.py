@@ -91,19 +91,54 @@ class _OnlineTargetFn(torch.autograd.Function):
         return None, None, None, None
 
 
+class _GraphedOnlineTargetFn(torch.autograd.Function):
+    """Same node as _OnlineTargetFn, but both passes are CUDA-graph replays over fixed buffers
+    (engine.Engine.graphed_step).  The returned tensors alias step-persistent buffers: they are valid until the next
+    training forward (the reference's loop consumes them immediately, main.py:589-617)."""
+
+    @staticmethod
+    def forward(ctx, model, gs, anchor):
+        from ._lib import launch_count
+        gs.fwd.replay()
+        gs.pending = True
+        launch_count[0] += gs.fwd_launches
+        ctx.model, ctx.gs = model, gs
+        ctx.set_materialize_grads(False)
+        flat = [t.detach() for t in gs.outs]
+        ctx.mark_non_differentiable(*flat[6:])
+        return tuple(flat)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        from ._lib import launch_count
+        eng, gs = ctx.model._engine, ctx.gs
+        gs.pending = False
+        d_reps, d_projs, d_preds = [grads[0], grads[3]], [grads[1], grads[4]], [grads[2], grads[5]]
+        if all(g is None for g in d_reps + d_projs) and all(g is not None for g in d_preds):
+            eng.notify_backward()
+            gs.d_pred[0].copy_(d_preds[0])
+            gs.d_pred[1].copy_(d_preds[1])
+            gs.bwd.replay()
+            launch_count[0] += gs.bwd_launches
+        else:
+            # unusual gradient pattern (e.g. a loss on the projections): eager kernels over the same saved buffers
+            eng.backward_online(gs.saved, d_reps, d_projs, d_preds)
+        return None, None, None
+
+
 class _ClassifierFn(torch.autograd.Function):
     """Stop-gradient linear classifier (main.py:250-252): logits are differentiable w.r.t. its own weights only."""
 
     @staticmethod
-    def forward(ctx, model, rep_cat_b, anchor):
+    def forward(ctx, model, rep_cat_b, anchor, logits=None):
         ctx.model = model
         ctx.rep = rep_cat_b
-        return model._engine.classifier_forward(rep_cat_b)
+        return model._engine.classifier_forward(rep_cat_b) if logits is None else logits.detach()
 
     @staticmethod
     def backward(ctx, d_logits):
         ctx.model._engine.classifier_backward(ctx.rep, d_logits)
-        return None, None, None
+        return None, None, None, None
 
 
 class BYOL(nn.Module):
@@ -175,9 +210,24 @@ class BYOL(nn.Module):
         eng = self._ensure_ready(b)
         a1 = augmentation1.contiguous().float()
         a2 = augmentation2.contiguous().float()
-        eng.prep_weights(eng.theta, eng.w_online, want_dgrad=self.training)
-        eng.prep_weights(self.target_network.mean, eng.w_target, want_dgrad=False)
-        if self.training and torch.is_grad_enabled():
+        gs = eng.graphed_step(self, a1, a2) if (self.training and torch.is_grad_enabled()) else None
+        if gs is not None and gs.mean_ptr != self.target_network.mean.data_ptr():
+            eng.graphs = {}          # the EMA buffer was replaced (e.g. load_state_dict with assign): re-capture later
+            gs = None
+        if gs is not None and gs.pending:
+            gs = None                # a graphed forward still awaits its backward: its fixed buffers must survive
+        if gs is not None:
+            # the whole forward (weight layouts, 4 lanes, classifier) is one graph launch over fixed buffers
+            eng.convert_inputs([a1], outs=gs.inputs[0:1])
+            eng.convert_inputs([a2], outs=gs.inputs[1:2])
+            o = _GraphedOnlineTargetFn.apply(self, gs, self._anchor)
+            linear_preds = _ClassifierFn.apply(self, self._rep_cat, self._anchor, gs.logits)
+        else:
+            eng.prep_weights(eng.theta, eng.w_online, want_dgrad=self.training)
+            eng.prep_weights(self.target_network.mean, eng.w_target, want_dgrad=False)
+        if gs is not None:
+            pass
+        elif self.training and torch.is_grad_enabled():
             o = _OnlineTargetFn.apply(self, a1, a2, self._anchor)
             rep_cat = self._rep_cat
             linear_preds = _ClassifierFn.apply(self, rep_cat, self._anchor)

@@ -57,11 +57,12 @@ def stem4_supported(cin, cout, h, w, k, stride, pad):
     return bool(lib.byol_stem4_supported(cin, cout, h, w, k, stride, pad))
 
 
-def nchw_to_stem4(x):
+def nchw_to_stem4(x, out=None):
     """fp32 NCHW [N, C<=4, H, W] -> zero-padded bf16 NHWC4 [N, H+6, Wp, 4] (input format of the stem kernels)."""
     _chk(x, F32, "x")
     n, c, h, w = x.shape
-    out = torch.empty((n, h + 6, lib.byol_stem4_row_pixels(), 4), dtype=BF16, device=x.device)
+    if out is None:
+        out = torch.empty((n, h + 6, lib.byol_stem4_row_pixels(), 4), dtype=BF16, device=x.device)
     check(lib.byol_nchw_to_stem4(_ptr(x), _ptr(out), n, c, h, w, _stream()), "byol_nchw_to_stem4")
     return out
 
