@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--image-size", type=int, default=224)
     ap.add_argument("--batch-per-gpu", type=int, default=512)
     ap.add_argument("--ref-batch", type=int, default=8, help="bounded sample batch for the CPU reference arm")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x2", "fp32"],
+                    help="forward arithmetic: bf16 operands (default) or the fp32-accurate split path (configs[1])")
     ap.add_argument("--no-sync-bn", action="store_true")
     ap.add_argument("--no-layers", action="store_true", help="skip the per-layer kernel roofline pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -255,7 +257,7 @@ def main_b200(args):
 
     torch.manual_seed(0)
     rep = REP_DIM.get(args.arch, 2048)
-    model = BYOL(rep, 256, 1000, total_training_steps=1000, arch=args.arch)
+    model = BYOL(rep, 256, 1000, total_training_steps=1000, arch=args.arch, precision=args.precision)
     sync_bn = world > 1 and not args.no_sync_bn
     if sync_bn:
         model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
@@ -380,13 +382,20 @@ def main_b200(args):
         line = {
             "metric": "images/sec", "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "vs_baseline": None, "data": "synthetic",
+            "dtype": "bf16" if args.precision == "bf16" else
+                     "fp32 forward via %d-term bf16 split products (fp32 accumulate, fp64 BN statistics); bf16-operand "
+                     "backward" % (6 if args.precision == "fp32" else 3),
             "config": {"workload": "%s BYOL training step, %dx%d, global batch %d (%d/GPU), %s, LARS+SGD momentum, "
                                    "EMA target; inputs (%.0f MB/step/GPU) larger than L2"
                                    % (args.arch, R, R, gb, b, "SyncBN + flat grad all-reduce" if sync_bn else
                                       "local BN", (aug1.numel() + aug2.numel()) * 4 / 1e6),
                        "global_batch": gb, "image_size": R, "parallelism": "dp%d" % world,
-                       "compute": "bf16 tensor-core inputs, fp32 accumulate / master weights / BN / loss / optimizer"},
+                       "compute": "bf16 tensor-core inputs, fp32 accumulate / master weights / BN / loss / optimizer"
+                                  if args.precision == "bf16" else
+                                  "fp32-accurate forward (precision=%s, csrc/split.cu), bf16-operand backward, fp32 "
+                                  "master weights / loss / optimizer" % args.precision,
+                       "cuda_graphs": bool(model._engine.use_graphs)},
             "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,

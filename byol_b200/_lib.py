@@ -65,6 +65,18 @@ _SIGNATURES = {
     "byol_ce_topk_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_void_p],
     "byol_ce_bwd": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
+    # fp32-accurate ("split-bf16") forward path, csrc/split.cu
+    "byol_split_planes": [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p],
+    "byol_nchw_to_planes": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "byol_prep_weight_planes": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "byol_stats_f32": [c_void_p, c_void_p, c_int64, c_int, c_void_p],
+    "byol_bn_finalize_lanes_f64": [c_void_p, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_int,
+                                   c_void_p],
+    "byol_bn_apply_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
+    "byol_maxpool_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "byol_avgpool_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "byol_abi_version": [],
     "byol_device_sm_count": [],
 }

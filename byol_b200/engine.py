@@ -86,6 +86,25 @@ class _Weights(object):
         self.w_stem4 = torch.empty(7 * 4 * 64 * 8, dtype=BF16, device=device) if self.stem4_ok else None
 
 
+class _SplitWeights(object):
+    """Weight-side plane layouts of one parameter set for the fp32-accurate forward path (csrc/split.cu):
+    per conv / linear a bf16 [Cout, taps * T * Cpad] matrix."""
+
+    def __init__(self, units, device, T):
+        self.T = T
+        sizes = [u.cout * u.k * u.k * T * u.cpad for u in units]
+        self.pool = torch.empty(sum(sizes), dtype=BF16, device=device)
+        self.w, off = [], 0
+        for u, n in zip(units, sizes):
+            self.w.append(self.pool[off:off + n].view(u.cout, u.k * u.k * T * u.cpad))
+            off += n
+
+    def prepare(self, units, flat):
+        for u in units:
+            w = flat[u.w_off:u.w_off + u.w_numel].view(u.cout, u.cin, u.k * u.k)
+            ops.prep_weight_planes(w, self.T, u.cpad, self.w[u.idx])
+
+
 class _Pool(object):
     """Bump allocator over one fp32 tensor (one memset / allocation per pass instead of one per layer)."""
 
@@ -124,6 +143,10 @@ class Engine(object):
         # BYOL_B200_GRAPHS=0 keeps every launch eager (debugging / profiling single kernels)
         self.use_graphs = os.environ.get("BYOL_B200_GRAPHS", "1") != "0"
         self.graphs = {}
+        # forward precision: 0 = bf16 operands (fast path); 3 / 6 = fp32 operands split into 3 / 6 bf16 product
+        # terms (~16 / 24 mantissa bits), fp32 conv outputs, fp64 BatchNorm statistics (csrc/split.cu)
+        self.T = 0
+        self.s_online = self.s_target = None
 
     # ------------------------------------------------------------------------------------------
     # flat buffers
@@ -262,6 +285,10 @@ class Engine(object):
         self.w_online = _Weights(self.units, self.device, True)
         self.w_target = _Weights(self.units, self.device, False)
         self.graphs = {}           # captured steps point into the old buffers
+        self.s_online = self.s_target = None
+        if self.T:
+            self.s_online = _SplitWeights(self.units, self.device, self.T)
+            self.s_target = _SplitWeights(self.units, self.device, self.T)
         self.ready = True
 
     def _module_key(self):
@@ -399,9 +426,10 @@ class Engine(object):
                 # padded NHWC4 for the dedicated stem kernels, NHWC8 for the generic path (e.g. 384x384 images)
                 use4 = self.w_online.stem4_ok and ops.stem4_supported(st.cin, st.cout, a.shape[2], a.shape[3], st.k,
                                                                       st.stride, st.pad)
-                o = outs[i] if outs is not None else (None, None)
-                conv[id(a)] = (None, ops.nchw_to_stem4(a, out=o[1]), a.shape[2], a.shape[3]) if use4 else \
-                    (ops.nchw_to_nhwc8(a, out=o[0]), None, a.shape[2], a.shape[3])
+                o = outs[i] if outs is not None else (None, None, 0, 0, None)
+                pl = ops.nchw_to_planes(a, self.T, st.cpad, out=o[4]) if self.T else None
+                conv[id(a)] = (None, ops.nchw_to_stem4(a, out=o[1]), a.shape[2], a.shape[3], pl) if use4 else \
+                    (ops.nchw_to_nhwc8(a, out=o[0]), None, a.shape[2], a.shape[3], pl)
             res.append(conv[id(a)])
         return res
 
@@ -417,6 +445,11 @@ class Engine(object):
         main = torch.cuda.current_stream()
         if x8 is None:
             x8 = self.convert_inputs(augs)
+        if self.T:
+            res, reps_b = self._forward_split(x8, lanes, train, rep_bf16_out or [None] * L)
+            if train:
+                torch._foreach_add_([b.num_batches_tracked for b in self.bn_modules], L)
+            return res, reps_b
         if rep_bf16_out is None:
             rep_bf16_out = [None] * L
         # under SyncBatchNorm the per-layer all-reduces serialise the lane pairs anyway: run all four lanes lock-step
@@ -486,6 +519,137 @@ class Engine(object):
         proj_f, proj_b = self._mlp_fwd(self.mlps[0], reps_b, lanes, train, "head")
         pred_f, _ = self._mlp_fwd(self.mlps[1], proj_b, lanes, train, "pred")
         return [(reps_f[i], proj_f[i], pred_f[i]) for i in range(L)], reps_b
+
+    # ------------------------------------------------------------------------------------------
+    # fp32-accurate forward ("split-bf16", csrc/split.cu): same layer walk, fp32 conv outputs, fp64 statistics.
+    # Lanes run lock-step on the caller's stream.  For the online lanes the bf16 tensors the (bf16) backward pass
+    # needs are written alongside, under the same keys as the fast path.
+    # ------------------------------------------------------------------------------------------
+    def _conv_bn_split(self, u, xs, lanes, train, is_linear=False):
+        L, C, T = len(lanes), u.cout, self.T
+        stats = torch.zeros(L * 2 * C, dtype=torch.float64, device=self.device) if train else None
+        ys = []
+        for i, (flat, _, _) in enumerate(lanes):
+            wset = self.s_online if flat is self.theta else self.s_target
+            bias = flat[u.b_off:u.b_off + C] if u.b_off >= 0 else None
+            if u.kind == "linear":
+                y = ops.linear_fprop(xs[i], wset.w[u.idx], bias=bias, out_fp32=True)
+            else:
+                y = ops.conv_fprop(xs[i], wset.w[u.idx], u.k, u.k, u.stride, u.pad, out_fp32=True)
+            if train:
+                ops.stats_f32(y.view(-1, C), stats[i * 2 * C:(i + 1) * 2 * C])
+            ys.append(y)
+        coeffs = torch.empty((L, 4, C), dtype=F32, device=self.device)
+        bn = u.bn
+        if train:
+            rows = ys[0].numel() // C
+            count = rows
+            if self.sync and self.world() > 1:
+                comm.allreduce_sum_(stats)
+                count = rows * self.world()
+            ops.bn_finalize_lanes_f64(stats, count, [flat[u.g_off:u.g_off + C] for flat, _, _ in lanes],
+                                      [flat[u.beta_off:u.beta_off + C] for flat, _, _ in lanes], bn.running_mean,
+                                      bn.running_var, bn.momentum, bn.eps, coeffs)
+        else:
+            for i, (flat, _, _) in enumerate(lanes):
+                ops.bn_eval_coeffs(flat[u.g_off:u.g_off + C], flat[u.beta_off:u.beta_off + C], bn.running_mean,
+                                   bn.running_var, bn.eps, coeffs[i])
+        return ys, coeffs
+
+    def _act_split(self, y, c, keep, resid=None, rc=None, block_out=False):
+        """BN-apply (+ residual) + ReLU of one lane's fp32 conv output -> (fp32 | None, planes NHWC, bf16 copy, mask)."""
+        C = y.shape[-1]
+        o32, pl, cp, mask = ops.bn_apply_f32(y.view(-1, C), c[0], c[1], True, self.T,
+                                             resid=None if resid is None else resid.view(-1, C),
+                                             rscale=None if rc is None else rc[0],
+                                             rshift=None if rc is None else rc[1], want_out32=block_out,
+                                             want_planes=True, want_copy=keep, want_mask=keep and block_out)
+        shp = tuple(y.shape[:-1])
+        return (None if o32 is None else o32.view(shp + (C,)), pl.view(shp + (self.T * C,)),
+                None if cp is None else cp.view(shp + (C,)), mask)
+
+    def _block_fwd_split(self, b, X, lanes, train):
+        """X: per lane (fp32 block input, its planes, its bf16 copy or None)."""
+        L = len(lanes)
+        keep = [lanes[i][2] is not None for i in range(L)]
+        xs_p = [x[1] for x in X]
+        y1, c1 = self._conv_bn_split(b.c1, xs_p, lanes, train)
+        a1 = [self._act_split(y1[i], c1[i], keep[i]) for i in range(L)]
+        y2, c2 = self._conv_bn_split(b.c2, [a[1] for a in a1], lanes, train)
+        if b.kind == "bottleneck":
+            a2 = [self._act_split(y2[i], c2[i], keep[i]) for i in range(L)]
+            y3, c3 = self._conv_bn_split(b.c3, [a[1] for a in a2], lanes, train)
+            ylast, clast = y3, c3
+        else:
+            a2, y3, c3 = None, None, None
+            ylast, clast = y2, c2
+        if b.down is not None:
+            yd, cd = self._conv_bn_split(b.down, xs_p, lanes, train)
+            outs = [self._act_split(ylast[i], clast[i], keep[i], resid=yd[i], rc=cd[i], block_out=True)
+                    for i in range(L)]
+        else:
+            yd, cd = None, None
+            outs = [self._act_split(ylast[i], clast[i], keep[i], resid=X[i][0], block_out=True) for i in range(L)]
+        for i, (_, _, saved) in enumerate(lanes):
+            if saved is not None:
+                cb = ops.cast_bf16
+                saved["blocks"].append({
+                    "mask": outs[i][3], "xsub": None, "x": X[i][2], "y1": cb(y1[i]), "c1": c1[i], "a1": a1[i][2],
+                    "y2": cb(y2[i]), "c2": c2[i], "a2": a2[i][2] if a2 is not None else None,
+                    "y3": cb(y3[i]) if y3 is not None else None, "c3": c3[i] if c3 is not None else None,
+                    "yd": cb(yd[i]) if yd is not None else None, "cd": cd[i] if cd is not None else None,
+                    "out": outs[i][2]})
+        return [(o[0], o[1], o[2]) for o in outs]
+
+    def _mlp_fwd_split(self, mlp, X, lanes, train, key):
+        """X: per lane (planes [b, T*in], bf16 copy [b, in]); returns fp32 outputs [b, out]."""
+        l1, l2 = mlp
+        L = len(lanes)
+        h, c = self._conv_bn_split(l1, [x[0] for x in X], lanes, train)
+        outs = []
+        for i, (flat, _, saved) in enumerate(lanes):
+            wset = self.s_online if flat is self.theta else self.s_target
+            _, ap, ab, _ = ops.bn_apply_f32(h[i], c[i][0], c[i][1], True, self.T, want_planes=True,
+                                            want_copy=saved is not None)
+            outs.append(ops.linear_fprop(ap, wset.w[l2.idx], bias=flat[l2.b_off:l2.b_off + l2.cout], out_fp32=True))
+            if saved is not None:
+                saved[key] = {"x": X[i][1], "h": ops.cast_bf16(h[i]), "c": c[i], "a": ab}
+        return outs
+
+    def _forward_split(self, x8, lanes, train, rep_bf16_out):
+        L, T = len(lanes), self.T
+        st = self.stem
+        keep = [lanes[i][2] is not None for i in range(L)]
+        y0, c0 = self._conv_bn_split(st, [x[4] for x in x8], lanes, train)
+        X = []
+        for i, (_, _, saved) in enumerate(lanes):
+            C = st.cout
+            a0, _, _, _ = ops.bn_apply_f32(y0[i].view(-1, C), c0[i][0], c0[i][1], True, T, want_out32=True,
+                                           want_planes=False)
+            p32, idx = ops.maxpool_f32(a0.view(y0[i].shape), self.pool_k, self.pool_s, self.pool_p, want_idx=keep[i])
+            pl, cp = ops.split_planes(p32.view(-1, C), T, want_copy=keep[i])
+            shp = tuple(p32.shape[:-1])
+            X.append((p32, pl.view(shp + (T * C,)), None if cp is None else cp.view(shp + (C,))))
+            if saved is not None:
+                saved.update({"x8": x8[i][0] if x8[i][1] is None else (x8[i][1], x8[i][2], x8[i][3]),
+                              "y0": ops.cast_bf16(y0[i]), "c0": c0[i], "a0_shape": tuple(y0[i].shape),
+                              "pool_idx": idx, "blocks": []})
+        for b in self.blocks:
+            X = self._block_fwd_split(b, X, lanes, train)
+        reps_f, reps_b, M = [], [], []
+        for i in range(L):
+            n, h, w, c = X[i][0].shape
+            rep = ops.avgpool_f32(X[i][0])
+            pl, cp = ops.split_planes(rep, T, want_copy=True, copy_out=rep_bf16_out[i])
+            reps_f.append(rep)
+            reps_b.append(cp)
+            M.append((pl, cp))
+            if keep[i]:
+                lanes[i][2]["final_shape"] = (n, h, w, c)
+        proj = self._mlp_fwd_split(self.mlps[0], M, lanes, train, "head")
+        M2 = [ops.split_planes(p, T, want_copy=keep[i]) for i, p in enumerate(proj)]
+        pred = self._mlp_fwd_split(self.mlps[1], M2, lanes, train, "pred")
+        return [(reps_f[i], proj[i], pred[i]) for i in range(L)], reps_b
 
     # ------------------------------------------------------------------------------------------
     # backward building blocks (online lanes only)
@@ -693,7 +857,16 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------
     def graph_key(self, a1):
         return (tuple(a1.shape), self.world(), bool(self.sync), self.theta.data_ptr(), self.multi_stream,
-                self.overlap_wgrad)
+                self.overlap_wgrad, self.T)
+
+    def prep_step(self, mean, training):
+        """All weight layouts one forward (+ backward) needs, from the fp32 masters."""
+        self.prep_weights(self.theta, self.w_online, want_dgrad=training)
+        if self.T:
+            self.s_online.prepare(self.units, self.theta)
+            self.s_target.prepare(self.units, mean)
+        else:
+            self.prep_weights(mean, self.w_target, want_dgrad=False)
 
     def graphed_step(self, model, a1, a2):
         """Returns the captured step for this input geometry, or None while it is still warming up / if graphs are
@@ -732,11 +905,10 @@ class Engine(object):
         st.fwd = torch.cuda.CUDAGraph()
         n0 = launch_count[0]
         with torch.cuda.graph(st.fwd, pool=pool, capture_error_mode="thread_local"):
-            self.prep_weights(self.theta, self.w_online, want_dgrad=True)
-            self.prep_weights(mean, self.w_target, want_dgrad=False)
+            self.prep_step(mean, True)
             outs, _ = self.forward_lanes(None, lanes, True, rep_bf16_out=[rep_cat[:b], rep_cat[b:], None, None],
                                          x8=[st.inputs[0], st.inputs[1], st.inputs[0], st.inputs[1]])
-            st.logits = self.classifier_forward(rep_cat)
+            st.logits = self.classifier_forward(rep_cat, [outs[0][0], outs[1][0]])
         st.fwd_launches = launch_count[0] - n0
         st.outs = [t for o in outs for t in o]
         # backward for the usual gradient pattern: only the two online predictions receive a gradient
@@ -751,10 +923,14 @@ class Engine(object):
         return st
 
     # classifier (stop-grad input; main.py:250-252)
-    def classifier_forward(self, rep_cat_b):
+    def classifier_forward(self, rep_cat_b, reps_f32=None):
         u = self.cls
         flat = self.theta
-        return ops.linear_fprop(rep_cat_b, self.w_online.wf[u.idx], bias=flat[u.b_off:u.b_off + u.cout], out_fp32=True)
+        bias = flat[u.b_off:u.b_off + u.cout]
+        if self.T and reps_f32 is not None:
+            pl = torch.cat([ops.split_planes(r, self.T)[0] for r in reps_f32], 0)
+            return ops.linear_fprop(pl, self.s_online.w[u.idx], bias=bias, out_fp32=True)
+        return ops.linear_fprop(rep_cat_b, self.w_online.wf[u.idx], bias=bias, out_fp32=True)
 
     def classifier_backward(self, rep_cat_b, d_logits):
         self.notify_backward()

@@ -130,15 +130,15 @@ class _ClassifierFn(torch.autograd.Function):
     """Stop-gradient linear classifier (main.py:250-252): logits are differentiable w.r.t. its own weights only."""
 
     @staticmethod
-    def forward(ctx, model, rep_cat_b, anchor, logits=None):
+    def forward(ctx, model, rep_cat_b, anchor, logits=None, reps_f32=None):
         ctx.model = model
         ctx.rep = rep_cat_b
-        return model._engine.classifier_forward(rep_cat_b) if logits is None else logits.detach()
+        return model._engine.classifier_forward(rep_cat_b, reps_f32) if logits is None else logits.detach()
 
     @staticmethod
     def backward(ctx, d_logits):
         ctx.model._engine.classifier_backward(ctx.rep, d_logits)
-        return None, None, None, None
+        return None, None, None, None, None
 
 
 class BYOL(nn.Module):
@@ -148,7 +148,7 @@ class BYOL(nn.Module):
     are keyword arguments with the reference's defaults (main.py:57,63)."""
 
     def __init__(self, base_network_output_size, projection_output_size, classifier_output_size,
-                 total_training_steps, base_decay=0.996, arch="resnet50", head_latent_size=4096):
+                 total_training_steps, base_decay=0.996, arch="resnet50", head_latent_size=4096, precision="bf16"):
         super(BYOL, self).__init__()
         self.base_network_output_size = base_network_output_size
         self.arch = arch
@@ -177,6 +177,13 @@ class BYOL(nn.Module):
             self.target_network.mean = (1 - d0) * theta0 + d0 * torch.zeros_like(theta0)
         self.target_network.step = 1
         self._engine = Engine(self)
+        # forward arithmetic: "bf16" = bf16 tensor-core operands (fast path); "fp32" = the reference's fp32 results
+        # from exact 3-way bf16 splits of every operand (6 product terms, fp64 statistics; BASELINE configs[1]);
+        # "bf16x2" = 2-way splits (3 terms, ~16 mantissa bits).  The backward pass always uses bf16 operands.
+        if precision not in ("bf16", "bf16x2", "fp32"):
+            raise ValueError("precision must be 'bf16', 'bf16x2' or 'fp32', got %r" % (precision,))
+        self.precision = precision
+        self._engine.T = {"bf16": 0, "bf16x2": 3, "fp32": 6}[precision]
         self._anchor = None
         self._rep_cat = None
 
@@ -223,14 +230,13 @@ class BYOL(nn.Module):
             o = _GraphedOnlineTargetFn.apply(self, gs, self._anchor)
             linear_preds = _ClassifierFn.apply(self, self._rep_cat, self._anchor, gs.logits)
         else:
-            eng.prep_weights(eng.theta, eng.w_online, want_dgrad=self.training)
-            eng.prep_weights(self.target_network.mean, eng.w_target, want_dgrad=False)
+            eng.prep_step(self.target_network.mean, self.training)
         if gs is not None:
             pass
         elif self.training and torch.is_grad_enabled():
             o = _OnlineTargetFn.apply(self, a1, a2, self._anchor)
             rep_cat = self._rep_cat
-            linear_preds = _ClassifierFn.apply(self, rep_cat, self._anchor)
+            linear_preds = _ClassifierFn.apply(self, rep_cat, self._anchor, None, (o[0].detach(), o[3].detach()))
         else:
             lanes = [(eng.theta, eng.w_online, None), (eng.theta, eng.w_online, None),
                      (self.target_network.mean, eng.w_target, None), (self.target_network.mean, eng.w_target, None)]
@@ -238,7 +244,7 @@ class BYOL(nn.Module):
                                              rep_bf16_out=[self._rep_cat[:b], self._rep_cat[b:], None, None])
             o = [t for oo in outs for t in oo]
             rep_cat = self._rep_cat if self.training else self._rep_cat[:b]   # eval: view 1 only (main.py:250-251)
-            linear_preds = eng.classifier_forward(rep_cat)
+            linear_preds = eng.classifier_forward(rep_cat, [o[0], o[3]] if self.training else [o[0]])
 
         # Update the EMA parameters with the pre-update online weights (main.py:254-255)
         self.target_network(eng.theta)

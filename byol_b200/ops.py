@@ -425,3 +425,97 @@ def ce_bwd(logits, labels, row_lse, grad_out):
     check(lib.byol_ce_bwd(_ptr(logits), _ptr(labels), labels.numel(), _ptr(row_lse), _ptr(grad_out), r, c, logits.stride(0), _ptr(d), c,
                           _stream()), "byol_ce_bwd")
     return d
+
+
+# ------------------------------------------------------------------------------------------------
+# fp32-accurate forward path ("split-bf16"; csrc/split.cu)
+# ------------------------------------------------------------------------------------------------
+F64 = torch.float64
+
+
+def split_planes(x2d, T, cpad=None, want_copy=False, copy_out=None):
+    """fp32 [M, C] (unit column stride) -> bf16 planes [M, T*cpad] (+ the plain bf16 rounding [M, C])."""
+    if x2d.dtype != F32 or not x2d.is_cuda or x2d.stride(-1) != 1:
+        raise ValueError("split_planes: need a CUDA fp32 matrix with unit column stride")
+    m, c = x2d.shape
+    cpad = cpad or c
+    planes = torch.empty((m, T * cpad), dtype=BF16, device=x2d.device)
+    copy = copy_out if copy_out is not None else \
+        (torch.empty((m, c), dtype=BF16, device=x2d.device) if want_copy else None)
+    _chk(copy, BF16, "copy_out")
+    check(lib.byol_split_planes(_ptr(x2d), _ptr(planes), _ptr(copy), m, c, cpad, x2d.stride(0), T, _stream()),
+          "byol_split_planes")
+    return planes, copy
+
+
+def nchw_to_planes(x, T, cpad=8, out=None):
+    """fp32 NCHW [N, C<=cpad, H, W] -> bf16 NHWC planes [N, H, W, T*cpad]."""
+    _chk(x, F32, "x")
+    n, c, h, w = x.shape
+    if out is None:
+        out = torch.empty((n, h, w, T * cpad), dtype=BF16, device=x.device)
+    check(lib.byol_nchw_to_planes(_ptr(x), _ptr(out), n, c, h, w, cpad, T, _stream()), "byol_nchw_to_planes")
+    return out
+
+
+def prep_weight_planes(w, T, cpad, out):
+    """fp32 [Cout, Cin, KH, KW] / [out, in] -> bf16 [Cout, taps*T*cpad] with the weight-side plane pattern."""
+    _chk(w, F32, "w")
+    cout, cin = w.shape[0], w.shape[1]
+    taps = w.numel() // (cout * cin)
+    check(lib.byol_prep_weight_planes(_ptr(w), _ptr(out), cout, cin, cpad, taps, T, _stream()),
+          "byol_prep_weight_planes")
+    return out
+
+
+def stats_f32(y2d, stats64):
+    """stats64 (zeroed fp64 [2C]) += [column sums, column sums of squares] of the fp32 matrix y2d."""
+    _chk(y2d, F32, "y"); _chk(stats64, F64, "stats")
+    m, c = y2d.shape
+    check(lib.byol_stats_f32(_ptr(y2d), _ptr(stats64), m, c, _stream()), "byol_stats_f32")
+    return stats64
+
+
+def bn_finalize_lanes_f64(stats64, count, gammas, betas, running_mean, running_var, momentum, eps, coeffs):
+    L = len(gammas)
+    c = gammas[0].numel()
+    g = [_ptr(t) for t in gammas] + [0] * (4 - L)
+    b = [_ptr(t) for t in betas] + [0] * (4 - L)
+    check(lib.byol_bn_finalize_lanes_f64(_ptr(stats64), float(count), L, g[0], b[0], g[1], b[1], g[2], b[2], g[3],
+                                         b[3], _ptr(running_mean), _ptr(running_var), float(momentum), float(eps),
+                                         _ptr(coeffs), c, _stream()), "byol_bn_finalize_lanes_f64")
+    return coeffs
+
+
+def bn_apply_f32(y2d, scale, shift, relu, T, resid=None, rscale=None, rshift=None, want_out32=False, want_planes=True,
+                 want_copy=False, want_mask=False):
+    """act(y*scale + shift (+ residual)) on fp32 [M, C] -> (out32, planes [M, T*C], bf16 copy, mask bits)."""
+    _chk(y2d, F32, "y"); _chk(resid, F32, "resid")
+    m, c = y2d.shape
+    dev = y2d.device
+    out32 = torch.empty((m, c), dtype=F32, device=dev) if want_out32 else None
+    planes = torch.empty((m, T * c), dtype=BF16, device=dev) if want_planes else None
+    copy = torch.empty((m, c), dtype=BF16, device=dev) if want_copy else None
+    mask = torch.empty(m * c // 8, dtype=torch.uint8, device=dev) if want_mask else None
+    check(lib.byol_bn_apply_f32(_ptr(y2d), _ptr(scale), _ptr(shift), _ptr(resid), _ptr(rscale), _ptr(rshift),
+                                _ptr(out32), _ptr(planes), _ptr(copy), _ptr(mask), m, c, int(relu), T, _stream()),
+          "byol_bn_apply_f32")
+    return out32, planes, copy, mask
+
+
+def maxpool_f32(x, k=3, s=2, p=1, want_idx=True):
+    _chk(x, F32, "x")
+    n, h, w, c = x.shape
+    ho, wo = conv_out_size(h, k, s, p), conv_out_size(w, k, s, p)
+    y = torch.empty((n, ho, wo, c), dtype=F32, device=x.device)
+    idx = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=x.device) if want_idx else None
+    check(lib.byol_maxpool_f32(_ptr(x), _ptr(y), _ptr(idx), n, h, w, c, k, s, p, _stream()), "byol_maxpool_f32")
+    return y, idx
+
+
+def avgpool_f32(x):
+    _chk(x, F32, "x")
+    n, h, w, c = x.shape
+    y = torch.empty((n, c), dtype=F32, device=x.device)
+    check(lib.byol_avgpool_f32(_ptr(x), _ptr(y), n, h * w, c, _stream()), "byol_avgpool_f32")
+    return y

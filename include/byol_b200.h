@@ -151,6 +151,29 @@ int byol_ce_topk_fwd(const float* logits, const int64_t* labels, int label_rows,
 int byol_ce_bwd(const float* logits, const int64_t* labels, int label_rows, const float* row_lse, const float* grad_out, int R, int C,
                 int ld, float* dlogits, int ldd, byol_stream_t stream);
 
+/* ---- fp32-accurate forward path ("split-bf16", BASELINE.json configs[1]): the reference runs main.py:229-276 in
+ *      fp32; here every fp32 operand is split exactly into T bf16 planes (T = 3: ~16 bits, T = 6: 24 bits) that feed
+ *      the SAME tensor-core kernels as one GEMM over T*C channels (byol_conv_igemm with C := T*C, out_fp32 = 1);
+ *      BatchNorm statistics are accumulated in fp64.  See csrc/split.cu. ---- */
+int byol_split_planes(const float* x /* [M, C], pitch ldx */, void* planes /* bf16 [M, T*Cpad] */,
+                      void* copy_bf16 /* optional [M, C] */, int64_t M, int C, int Cpad, int ldx, int T,
+                      byol_stream_t stream);
+int byol_nchw_to_planes(const float* x /* NCHW */, void* planes /* bf16 NHWC [N,H,W,T*Cpad] */, int N, int Cin, int H,
+                        int W, int Cpad, int T, byol_stream_t stream);
+int byol_prep_weight_planes(const float* w /* [Cout, Cin, taps] */, void* out /* bf16 [Cout, taps*T*Cpad] */, int Cout,
+                            int Cin, int Cpad, int taps, int T, byol_stream_t stream);
+int byol_stats_f32(const float* y, double* stats /* zeroed [2C] */, int64_t M, int C, byol_stream_t stream);
+int byol_bn_finalize_lanes_f64(const double* stats, double count, int L, const float* gamma0, const float* beta0,
+                               const float* gamma1, const float* beta1, const float* gamma2, const float* beta2,
+                               const float* gamma3, const float* beta3, float* running_mean, float* running_var,
+                               float momentum, float eps, float* coeffs, int C, byol_stream_t stream);
+int byol_bn_apply_f32(const float* y, const float* scale, const float* shift, const float* resid, const float* rscale,
+                      const float* rshift, float* out32, void* planes, void* copy_bf16, void* mask, int64_t M, int C,
+                      int relu, int T, byol_stream_t stream);
+int byol_maxpool_f32(const float* x, float* y, void* idx, int N, int H, int W, int C, int k, int s, int p,
+                     byol_stream_t stream);
+int byol_avgpool_f32(const float* x, float* y, int N, int HW, int C, byol_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
