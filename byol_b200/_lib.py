@@ -77,6 +77,8 @@ _SIGNATURES = {
                           c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
     "byol_maxpool_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "byol_avgpool_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "byol_xchg_layout": [c_void_p, c_void_p, c_void_p],
+    "byol_xchg_sum": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p],
     "byol_abi_version": [],
     "byol_device_sm_count": [],
 }

@@ -663,8 +663,8 @@ class Engine(object):
         rows = ys[0].numel() // C
         count, local = rows, None
         if self.sync and self.world() > 1:
-            local = s12.clone()
-            comm.allreduce_sum_(s12)
+            local = torch.empty_like(s12)
+            comm.allreduce_sum_(s12, local_out=local)
             count = rows * self.world()
         gamma = self.theta[u.g_off:u.g_off + C]
         dys, dzs = [], []
@@ -877,6 +877,8 @@ class Engine(object):
         launches plus a handful of small eager kernels (input layout, loss, EMA, LARS) on the host."""
         if not self.use_graphs:
             return None
+        if self.sync and comm.uses_nccl_for_statistics(self.device):
+            return None          # per-layer NCCL collectives stay eager; the peer-memory exchange is capturable
         key = self.graph_key(a1)
         st = self.graphs.get(key)
         if st is None:

@@ -174,6 +174,13 @@ int byol_maxpool_f32(const float* x, float* y, void* idx, int N, int H, int W, i
                      byol_stream_t stream);
 int byol_avgpool_f32(const float* x, float* y, int N, int HW, int C, byol_stream_t stream);
 
+/* ---- SyncBatchNorm statistic exchange over NVLink peer memory (main.py:433; replaces the per-layer all_gather /
+ *      all_reduce of torch/nn/modules/_functions.py:49-74,158-159): one single-CTA kernel per exchange — publish into
+ *      this rank's symmetric buffer, flag every peer, wait, add all peers' values in rank order.  See csrc/xchg.cu. */
+int byol_xchg_layout(int* slots, int* max_world, int* flag_bytes);
+int byol_xchg_sum(void* vals, void* local_copy, int n, int is_f64, const uint64_t* peer_ptrs /* host, [world] */,
+                  int world, int rank, int64_t cap_bytes, void* counter /* device uint32 */, byol_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
