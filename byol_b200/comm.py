@@ -54,12 +54,15 @@ class PeerExchange(object):
         return t
 
 
+NUM_CHANNELS = 2      # independent exchange sequences: one per CUDA stream that carries SyncBatchNorm layers
 _peer = {"tried": False, "xchg": None}
 
 
 def peer_exchange(device=None, cap_bytes=1 << 19):
-    """The process-wide PeerExchange (created on first use, collectively: every rank must call it at the same point),
-    or None when it is disabled (BYOL_B200_PEER_XCHG=0), unavailable (no NCCL / symmetric memory) or world == 1."""
+    """The process-wide list of PeerExchange channels (created on first use, collectively: every rank must call it at
+    the same point), or None when disabled (BYOL_B200_PEER_XCHG=0), unavailable (no NCCL / symmetric memory) or
+    world == 1.  Each channel has its own buffer and sequence counter, so two streams (the online / target lane pairs
+    of the forward pass, the two views of the backward pass) can exchange concurrently."""
     if _peer["tried"]:
         return _peer["xchg"]
     _peer["tried"] = True
@@ -67,7 +70,7 @@ def peer_exchange(device=None, cap_bytes=1 << 19):
         return None
     ok = torch.ones(1, device=device)
     try:
-        x = PeerExchange(device, cap_bytes)
+        x = [PeerExchange(device, cap_bytes) for _ in range(NUM_CHANNELS)]
     except Exception as e:      # symmetric memory needs P2P / fabric handles; fall back to NCCL on ALL ranks
         print("[byol_b200] peer exchange unavailable (%s: %s); SyncBatchNorm statistics use NCCL" % (type(e).__name__, e))
         x = None
@@ -77,12 +80,13 @@ def peer_exchange(device=None, cap_bytes=1 << 19):
     return _peer["xchg"]
 
 
-def allreduce_sum_(t, local_out=None):
-    """In-place SUM over ranks of a small statistics vector; local_out (optional) receives this rank's input."""
+def allreduce_sum_(t, local_out=None, channel=0):
+    """In-place SUM over ranks of a small statistics vector; local_out (optional) receives this rank's input.
+    `channel` selects the exchange sequence (all ranks must use the same channel for the same exchange)."""
     if world_size() > 1:
         x = peer_exchange(t.device) if t.is_cuda else None
-        if x is not None and t.numel() * t.element_size() <= x.cap_bytes:
-            return x.sum_(t, local_out)
+        if x is not None and t.numel() * t.element_size() <= x[channel].cap_bytes:
+            return x[channel].sum_(t, local_out)
         if local_out is not None:
             local_out.copy_(t)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)

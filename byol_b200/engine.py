@@ -134,12 +134,13 @@ class Engine(object):
         self._side_stream = None
         self._side_used = False
         self._side_refs = []
-        self.overlap_wgrad = True
-        self.multi_stream = True
+        self.overlap_wgrad = os.environ.get("BYOL_B200_OVERLAP_WGRAD", "1") != "0"
+        self.multi_stream = os.environ.get("BYOL_B200_MULTI_STREAM", "1") != "0"
         self._fwd_streams = None
         self._bwd_streams = None
         self._fin_events = None
         self._group_order = 0
+        self._bwd_channel = 0
         # BYOL_B200_GRAPHS=0 keeps every launch eager (debugging / profiling single kernels)
         self.use_graphs = os.environ.get("BYOL_B200_GRAPHS", "1") != "0"
         self.graphs = {}
@@ -340,7 +341,7 @@ class Engine(object):
             rows = ys[0].numel() // C
             count = rows
             if self.sync and self.world() > 1:
-                comm.allreduce_sum_(stats)
+                comm.allreduce_sum_(stats, channel=self._group_order)
                 count = rows * self.world()
             fin = self._fin_events
             if fin is not None and self._group_order == 1:
@@ -452,9 +453,10 @@ class Engine(object):
             return res, reps_b
         if rep_bf16_out is None:
             rep_bf16_out = [None] * L
-        # under SyncBatchNorm the per-layer all-reduces serialise the lane pairs anyway: run all four lanes lock-step
-        # on one stream there, which halves the number of (latency-bound) NCCL calls
-        two = self.multi_stream and L == 4 and not (self.sync and self.world() > 1)
+        # under SyncBatchNorm over NCCL the per-layer all-reduces serialise the lane pairs anyway: run all four lanes
+        # lock-step on one stream there, which halves the number of (latency-bound) NCCL calls.  The peer-memory
+        # exchange (comm.PeerExchange) has one channel per stream, so the two-stream schedule stays.
+        two = self.multi_stream and L == 4 and not (self.sync and comm.uses_nccl_for_statistics(self.device))
         groups = [(list(range(0, 2)), self._fwd_streams[0]), (list(range(2, 4)), self._fwd_streams[1])] if two \
             else [(list(range(L)), main)]
         self._fin_events = {} if (two and train) else None
@@ -664,7 +666,7 @@ class Engine(object):
         count, local = rows, None
         if self.sync and self.world() > 1:
             local = torch.empty_like(s12)
-            comm.allreduce_sum_(s12, local_out=local)
+            comm.allreduce_sum_(s12, local_out=local, channel=self._bwd_channel)
             count = rows * self.world()
         gamma = self.theta[u.g_off:u.g_off + C]
         dys, dzs = [], []
@@ -797,7 +799,8 @@ class Engine(object):
             self.notify_backward()
         L = len(saved)
         main = torch.cuda.current_stream()
-        if not (self.multi_stream and L == 2) or (self.sync and self.world() > 1):
+        if not (self.multi_stream and L == 2) or (self.sync and comm.uses_nccl_for_statistics(self.device)):
+            self._bwd_channel = 0
             self._backward_group(saved, d_reps, d_projs, d_preds)
             return
         ev = torch.cuda.Event()
@@ -806,6 +809,7 @@ class Engine(object):
             stream = self._bwd_streams[i]
             stream.wait_event(ev)
             with torch.cuda.stream(stream):
+                self._bwd_channel = i      # one exchange channel per view / stream
                 self._backward_group([saved[i]], [d_reps[i]], [d_projs[i]], [d_preds[i]])
         for i in range(L):
             e2 = torch.cuda.Event()
