@@ -96,27 +96,82 @@ class ClockSampler(object):
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm / cpu_baseline (the ONLY place bench.py touches oracle/)
 # ------------------------------------------------------------------------------------------------
-def run_cpu_reference(arch, image_size, batch, steps, warmup):
-    """The reference algorithm (oracle port of main.py's step, pinned against the real reference) on the host
-    cores, on a bounded sample of the workload: `batch` images per step at the same geometry."""
+def _host_threads():
+    """All host cores: torchrun exports OMP_NUM_THREADS=1 for its workers, which would silently turn the CPU arm into
+    a single-thread run."""
     import torch
-    from oracle import byol_oracle as O
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
+def _run_reference_main(arch, image_size, batch, steps, warmup):
+    """The UNMODIFIED reference (baseline/_ref/main.py, shipped by tools/ship_reference.py) on the host cores: its
+    BYOL / loss_function / LARS(SGD) driven by its own main.execute_graph, --no-cuda, synthetic batches."""
+    import torch
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref, "main.py")):
+        return None
+    rep = REP_DIM.get(arch, 2048)
+    argv, path = sys.argv, list(sys.path)
+    sys.argv = ["main.py", "--arch=%s" % arch, "--representation-size=%d" % rep, "--num-replicas=1", "--no-cuda",
+                "--batch-size=%d" % batch, "--image-size-override=%d" % image_size]
+    sys.path[:0] = [ref, os.path.join(ROOT, "oracle", "ref_shims")]
+    try:
+        import main
+    finally:
+        sys.argv, sys.path[:] = argv, path
+    main.args.cuda, main.args.distributed_rank = False, 0
+    from helpers import layers
+    from optimizers.lars import LARS
     torch.manual_seed(0)
-    params, buffers = O.init_reference_state(arch, 0)
-    model = O.OracleBYOL(arch, params, buffers, 1000)
+    model = main.BYOL(base_network_output_size=rep, projection_output_size=256, classifier_output_size=1000,
+                      total_training_steps=1000, base_decay=0.996)
+    opt = LARS(torch.optim.SGD(layers.add_weight_decay(model, 1e-6), lr=0.2 * batch / 256, momentum=0.9), eps=0.0)
     g = torch.Generator().manual_seed(1234)
-    a1 = torch.rand(batch, 3, image_size, image_size, generator=g)
-    a2 = torch.rand(batch, 3, image_size, image_size, generator=g)
-    lab = torch.randint(0, 1000, (batch,), generator=g)
-    for _ in range(warmup):
-        model.train_step(a1, a2, lab, 0.2 * batch / 256)
+    bt = (torch.rand(batch, 3, image_size, image_size, generator=g),
+          torch.rand(batch, 3, image_size, image_size, generator=g), torch.randint(0, 1000, (batch,), generator=g))
+    if warmup:
+        main.execute_graph(0, model, [bt] * warmup, None, optimizer=opt, prefix="train")
     t0 = time.perf_counter()
-    for _ in range(steps):
-        model.train_step(a1, a2, lab, 0.2 * batch / 256)
-    dt = time.perf_counter() - t0
-    return {"value": steps * batch / dt, "unit": "images/sec", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "%d step(s) of %s BYOL at batch %d, %dx%d, fp32, torch CPU (oracle/byol_oracle.py)"
-                      % (steps, arch, batch, image_size, image_size), "ms_per_step": 1000 * dt / steps}
+    main.execute_graph(1, model, [bt] * steps, None, optimizer=opt, prefix="train")
+    return time.perf_counter() - t0
+
+
+def run_cpu_reference(arch, image_size, batch, steps, warmup):
+    """The reference's own CPU implementation of the step on all host cores, on a bounded sample of the workload
+    (`batch` images per step at the same geometry): the unmodified reference when it was shipped to this box
+    (kind "reference"), else the oracle port of main.py's step, which is pinned against it (kind "port")."""
+    import contextlib
+    import io
+    import torch
+    cores = _host_threads()
+    kind, what = "reference", "unmodified /root/reference main.execute_graph (baseline/_ref)"
+    with contextlib.redirect_stdout(io.StringIO()):        # the reference prints a log line per call
+        dt = _run_reference_main(arch, image_size, batch, steps, warmup)
+    if dt is None:
+        from oracle import byol_oracle as O
+        kind, what = "port", "oracle/byol_oracle.py"
+        torch.manual_seed(0)
+        params, buffers = O.init_reference_state(arch, 0)
+        model = O.OracleBYOL(arch, params, buffers, 1000)
+        g = torch.Generator().manual_seed(1234)
+        a1 = torch.rand(batch, 3, image_size, image_size, generator=g)
+        a2 = torch.rand(batch, 3, image_size, image_size, generator=g)
+        lab = torch.randint(0, 1000, (batch,), generator=g)
+        for _ in range(warmup):
+            model.train_step(a1, a2, lab, 0.2 * batch / 256)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            model.train_step(a1, a2, lab, 0.2 * batch / 256)
+        dt = time.perf_counter() - t0
+    return {"value": steps * batch / dt, "unit": "images/sec", "cores": cores, "kind": kind,
+            "sample": "%d step(s) of %s BYOL at batch %d, %dx%d, fp32, torch CPU, %d threads (%s)"
+                      % (steps, arch, batch, image_size, image_size, cores, what), "ms_per_step": 1000 * dt / steps}
 
 
 def main_reference(args):

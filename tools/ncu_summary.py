@@ -19,7 +19,8 @@ KEYS = [
 ]
 
 
-def launches(path):
+def launches(path, json_out=None):
+    """Per-kernel launch count, time share and (when the capture has them) DRAM bytes."""
     rows = list(csv.reader(open(path)))
     hdr, agg, n = None, collections.OrderedDict(), 0
     for r in rows:
@@ -29,20 +30,38 @@ def launches(path):
         if hdr is None or len(r) != len(hdr):
             continue
         d = dict(zip(hdr, r))
-        if d.get("Metric Name") != "gpu__time_duration.sum":
+        metric = d.get("Metric Name")
+        if metric not in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum"):
             continue
         name = re.sub(r"<.*", "", d["Kernel Name"]).split("(")[0].replace("void ", "")
-        v, unit = float(d["Metric Value"].replace(",", "")), d["Metric Unit"]
-        v = v / 1e3 if unit.startswith("n") else (v * 1e3 if unit.startswith("m") else v)
-        a = agg.setdefault(name, [0, 0.0])
-        a[0] += 1
-        a[1] += v
-        n += 1
+        v, unit = float(d["Metric Value"].replace(",", "")), d["Metric Unit"].lower()
+        a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])      # launches, us, bytes read, bytes written
+        if metric == "gpu__time_duration.sum":
+            v = v / 1e3 if unit.startswith("n") else (v * 1e3 if unit.startswith("m") else v)
+            a[0] += 1
+            a[1] += v
+            n += 1
+        else:
+            mult = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+            a[2 if metric.endswith("read.sum") else 3] += v * mult
     tot = sum(a[1] for a in agg.values())
+    have_bytes = any(a[2] + a[3] > 0 for a in agg.values())
     print("launches captured: %d, sum of durations: %.1f us (cold-cache, serialised: compare SHARES)\n" % (n, tot))
-    print("| kernel | launches | total us | share |\n|---|---:|---:|---:|")
+    if have_bytes:
+        print("| kernel | launches | total us | share | DRAM read GB | DRAM write GB | GB/s |\n|---|---:|---:|---:|---:|---:|---:|")
+    else:
+        print("| kernel | launches | total us | share |\n|---|---:|---:|---:|")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print("| %s | %d | %.1f | %.1f%% |" % (k, a[0], a[1], 100 * a[1] / tot))
+        if have_bytes:
+            print("| %s | %d | %.1f | %.1f%% | %.2f | %.2f | %.0f |" % (k, a[0], a[1], 100 * a[1] / tot, a[2] / 1e9,
+                                                                  a[3] / 1e9, (a[2] + a[3]) / 1e3 / max(a[1], 1e-9)))
+        else:
+            print("| %s | %d | %.1f | %.1f%% |" % (k, a[0], a[1], 100 * a[1] / tot))
+    if json_out:
+        import json
+        with open(json_out, "w") as f:
+            json.dump({k: {"launches": a[0], "us": a[1], "dram_read_bytes": a[2], "dram_write_bytes": a[3]}
+                       for k, a in agg.items()}, f, indent=1)
 
 
 def report(paths):
@@ -64,6 +83,6 @@ def report(paths):
 
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
-        launches(sys.argv[2])
+        launches(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
     else:
         report(sys.argv[2:])
