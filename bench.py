@@ -31,6 +31,15 @@ ALG_GFLOP_PER_IMAGE = {("resnet50", 224): 65.1067, ("resnet18", 224): 28.6288, (
 REP_DIM = {"resnet18": 512, "resnet34": 512}
 
 
+_T0 = time.perf_counter()
+
+
+def note(msg):
+    """Progress on stderr (the JSON line on stdout stays alone)."""
+    sys.stderr.write("[bench %7.1fs] %s\n" % (time.perf_counter() - _T0, msg))
+    sys.stderr.flush()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -97,15 +106,17 @@ class ClockSampler(object):
 # CPU reference arm / cpu_baseline (the ONLY place bench.py touches oracle/)
 # ------------------------------------------------------------------------------------------------
 def _host_threads():
-    """All host cores: torchrun exports OMP_NUM_THREADS=1 for its workers, which would silently turn the CPU arm into
-    a single-thread run."""
+    """Threads for the CPU arm.  torchrun exports OMP_NUM_THREADS=1 for its workers, which would silently turn the CPU
+    arm into a single-thread run; all 128 hyper-threads of the GPU box, on the other hand, make the eager reference
+    ~20x SLOWER than 64 (measured: oversubscribed OpenMP spin-waits around its many tiny ops).  So: one thread per
+    physical core (half the visible CPUs), at most 64 — the count torch itself picks on that box."""
     import torch
     n = os.cpu_count() or 1
     try:
         n = len(os.sched_getaffinity(0))
     except Exception:
         pass
-    torch.set_num_threads(max(1, n))
+    torch.set_num_threads(max(1, min(64, n // 2 if n > 8 else n)))
     return torch.get_num_threads()
 
 
@@ -338,6 +349,7 @@ def main_b200(args):
         return ms
 
     # ---- device-resident timing ---------------------------------------------------------------
+    note("model built; warm-up")
     for _ in range(args.warmup):
         wiring.train_step(net, opt, aug1, aug2, labels)
     barrier()
@@ -364,6 +376,7 @@ def main_b200(args):
     loss_val = float(stats["loss_mean"].item())
     value = args.steps * gb / (ms / 1000.0)
 
+    note("device-resident timing done: %.2f ms/step" % (ms / args.steps))
     # ---- end to end: pinned host inputs -> H2D -> step -> D2H loss, every step ------------------
     h1, h2 = aug1.cpu().pin_memory(), aug2.cpu().pin_memory()
     hl = labels.cpu().pin_memory()
@@ -406,6 +419,7 @@ def main_b200(args):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = args.steps * gb / (ms_e2e / 1000.0)
 
+    note("end-to-end timing done: %.2f ms/step" % (ms_e2e / args.steps))
     # ---- roofline --------------------------------------------------------------------------------
     alg = ALG_GFLOP_PER_IMAGE.get((args.arch, R))
     step_tflops = (value / world) * alg / 1000.0 if alg else None
@@ -413,6 +427,23 @@ def main_b200(args):
                 "frac": (step_tflops / peak_sustained) if step_tflops else None, "traffic": None,
                 "what": "whole step: images/s/GPU x %.4f algorithmic GFLOP/image vs sustained bf16 peak, %s"
                         % (alg or 0.0, peak_src)}
+    # DRAM traffic of one step from the committed ncu launch list (profiles/traffic_r02.json: dram__bytes_read.sum +
+    # dram__bytes_write.sum per launch, summed over one eager step of this same command) - only for the workload it
+    # was captured on
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json")))
+        if (args.arch, R, b, args.precision) == ("resnet50", 224, 512, "bf16"):
+            traffic = tr
+    except Exception:
+        pass
+    if traffic is not None:
+        roofline["traffic"] = traffic["step_dram_bytes"]
+        hbm_peak = peaks.get("hbm_gbs", 6485.8)
+        gbs = traffic["step_dram_bytes"] / (ms / args.steps / 1000.0) / 1e9
+        roofline["hbm_view"] = {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                "what": "DRAM bytes of one step (ncu, profiles/traffic_r02.json) / measured step time: "
+                                        "in aggregate the step is bound by HBM traffic, not by the tensor pipe"}
     if rank == 0 and world == 1 and not args.no_layers:
         rows, agg = layer_table(model, b, R)
         conv_flops = sum(v["launch_gflop"] for v in agg.values())
@@ -422,6 +453,7 @@ def main_b200(args):
             "achieved": conv_flops / conv_ms, "peak": peak_burst, "unit": "TFLOP/s",
             "frac": conv_flops / conv_ms / peak_burst, "isolated_ms_per_step": conv_ms,
             "share_of_step": conv_ms / (ms / args.steps), "by_kind": agg,
+            "traffic": traffic["tcgen05_family_dram_bytes"] if traffic is not None else None,
             "how": "every distinct conv shape timed alone with CUDA events, L2 flushed between launches, weighted "
                    "by its count in one step (4 fprop passes, 2 dgrad/wgrad passes); peak = burst bf16, %s" % peak_src}
         if args.layers_out:
@@ -429,9 +461,20 @@ def main_b200(args):
                 json.dump({"batch": b, "image_size": R, "rows": rows, "agg": agg}, f, indent=1)
 
     cpu_baseline = None
+    note("per-layer table done")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = run_cpu_reference(args.arch, R, args.ref_batch, 1, 1)
-        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        # in a child process with a hard limit: a pathological host (thread oversubscription) must not stall the bench
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                                  "--warmup", "1", "--arch", args.arch, "--image-size", str(R), "--ref-batch",
+                                  str(args.ref_batch)], capture_output=True, text=True, timeout=240,
+                                 env={k: v for k, v in os.environ.items() if k != "OMP_NUM_THREADS"})
+            cpu_baseline = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            note("cpu baseline done: %s" % cpu_baseline["sample"])
+        except Exception as e:
+            cpu_baseline = {"value": None, "unit": "images/sec", "cores": None, "kind": "unavailable",
+                            "sample": "CPU arm did not finish within 240 s (%s)" % type(e).__name__}
+            note("cpu baseline failed: %r" % (e,))
 
     if rank == 0:
         line = {
