@@ -39,13 +39,6 @@ struct ConvGemmParams {
   const float* bias;   // optional, [Ndim]
   float* col_sum;      // optional, [Ndim] fp32: += sum over rows of the stored value
   float* col_sqsum;    // optional, [Ndim] fp32: += sum over rows of value^2
-  // ---- fused BatchNorm epilogue (FUSED kernel variants only; see byol_conv_igemm_fused) ----
-  const float* colscale;        // optional [Ndim]: t = acc * colscale + bias (BN scale/shift, or invstd / -mean*invstd)
-  const float* resid_colscale;  // optional [Ndim]: the (masked) residual term is multiplied per column
-  uint8_t* mask_out;            // optional: bit e of byte i = (stored element 8i + e > 0), same linear order as dst
-  int no_store;                 // 1: only the fused column statistics are produced, dst is not written
-  int bwd_reduce;               // 1: BatchNorm-backward sums of a RECOMPUTED conv output: with t = acc*colscale + bias
-                                //    (= xhat) and dz = resid masked by resid_mask: col_sum += sum dz, col_sqsum += sum dz*t
   int Nimg, Hs, Ws, C;
   int Ho, Wo;
   int KH, KW;
@@ -127,7 +120,7 @@ struct SmemLayout {
 //   next warp           : MMA issuer (+ TMEM alloc / dealloc)
 //   last warp           : barrier init + TMA producer
 // ---------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool A_TMA, bool FUSED>
+template <int BN, int STAGES, bool A_TMA>
 __global__ void __launch_bounds__(320, 2)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                   const __grid_constant__ CUtensorMap tmapC, const ConvGemmParams p, const int num_tiles) {
@@ -164,7 +157,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     fence_mbar_init();
     tma_prefetch_desc(&tmapB);
     if (A_TMA) tma_prefetch_desc(&tmapA);
-    if (!p.out_fp32 && !(FUSED && (p.no_store || p.bwd_reduce))) tma_prefetch_desc(&tmapC);
+    if (!p.out_fp32) tma_prefetch_desc(&tmapC);
   }
   if (warp == MMA_WARP) {
     tmem_alloc(tmem_slot, 2 * BN);
@@ -190,26 +183,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     uint64_t cs1[NACC], cs2[NACC];   // packed {even, odd} column sums / sums of squares
 #pragma unroll
     for (int i = 0; i < NACC; ++i) { cs1[i] = 0ull; cs2[i] = 0ull; }
-    // FUSED bwd_reduce mode: lane l owns column c0 + l of each of this warp's chunks (after a transpose-reduce)
-    float racc1[NACC], racc2[NACC];
-#pragma unroll
-    for (int i = 0; i < NACC; ++i) { racc1[i] = 0.f; racc2[i] = 0.f; }
-    const bool red_mode = FUSED && p.bwd_reduce;
     int local = 0;
     int stat_n0 = -1;   // column offset the register accumulators currently belong to
     auto flush_stats = [&]() {
-      if (red_mode) {
-#pragma unroll
-        for (int i = 0; i < NACC; ++i) {
-          const int col = stat_n0 + col_w0 + i * 32 + lane;
-          if (col < p.Ndim) {
-            atomicAdd(p.col_sum + col, racc1[i]);
-            atomicAdd(p.col_sqsum + col, racc2[i]);
-          }
-          racc1[i] = 0.f; racc2[i] = 0.f;
-        }
-        return;
-      }
 #pragma unroll
       for (int i = 0; i < NACC; ++i) {
         float2 a = f2_unpack(cs1[i]), b = f2_unpack(cs2[i]);
@@ -283,58 +259,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (FUSED && p.colscale != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nbase + j < p.Ndim) v[j] *= __ldg(p.colscale + nbase + j);
-        }
         if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (nbase + j < p.Ndim) v[j] += __ldg(p.bias + nbase + j);
-        }
-        if (FUSED && red_mode) {
-          // dz = incoming gradient masked by the ReLU bits; v = xhat of the recomputed conv output.  Column sums over
-          // this warp's 32 rows by a transpose-reduce: after the 5 exchange rounds lane l holds column l.
-          float dz[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) dz[j] = 0.f;
-          if (rvalid) {
-            const bf16* rp = p.resid + rrow * p.ldc + nbase;
-            const uint8_t* mp = p.resid_mask != nullptr ? p.resid_mask + ((rrow * p.ldc + nbase) >> 3) : nullptr;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (nbase + j < p.Ndim) {
-                uint4 q = *reinterpret_cast<const uint4*>(rp + j);
-                const uint32_t mb = mp != nullptr ? (uint32_t)__ldg(mp + (j >> 3)) : 0xffu;
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float2 f = __bfloat1622float2(h[e]);
-                  dz[j + 2 * e] = ((mb >> (2 * e)) & 1u) ? f.x : 0.f;
-                  dz[j + 2 * e + 1] = ((mb >> (2 * e + 1)) & 1u) ? f.y : 0.f;
-                }
-              }
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= dz[j];
-#pragma unroll
-          for (int o = 16, n = 32; o >= 1; o >>= 1, n >>= 1) {
-            const bool up = (lane & o) != 0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (j < n / 2) {
-                const float sd = up ? dz[j] : dz[j + n / 2], kd = up ? dz[j + n / 2] : dz[j];
-                const float sv = up ? v[j] : v[j + n / 2], kv = up ? v[j + n / 2] : v[j];
-                dz[j] = kd + __shfl_xor_sync(0xffffffffu, sd, o);
-                v[j] = kv + __shfl_xor_sync(0xffffffffu, sv, o);
-              }
-            }
-          }
-          racc1[cl] += dz[0];
-          racc2[cl] += v[0];
-          continue;
         }
         if (p.resid != nullptr && rvalid) {
           const bf16* rp = p.resid + rrow * p.ldc + nbase;
@@ -348,10 +276,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float2 f = __bfloat1622float2(h[e]);
-                if (FUSED && p.resid_colscale != nullptr) {
-                  f.x *= __ldg(p.resid_colscale + nbase + j + 2 * e);
-                  f.y *= __ldg(p.resid_colscale + nbase + j + 2 * e + 1);
-                }
                 v[j + 2 * e] += ((mb >> (2 * e)) & 1u) ? f.x : 0.f;
                 v[j + 2 * e + 1] += ((mb >> (2 * e + 1)) & 1u) ? f.y : 0.f;
               }
@@ -361,20 +285,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         if (p.relu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (FUSED && p.mask_out != nullptr && mvalid) {
-          // ReLU mask of the block output as bits (read by the backward pass instead of the activation)
-          uint32_t bits = 0u;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
-          uint8_t* mo = p.mask_out + (((int64_t)m * p.ldc + nbase) >> 3);
-          if ((p.ldc & 31) == 0 && nbase + 32 <= p.Ndim) {
-            *reinterpret_cast<uint32_t*>(mo) = bits;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (nbase + 8 * j < p.Ndim) mo[j] = (uint8_t)(bits >> (8 * j));
-          }
         }
         if (p.parity) {
           // rows of one tile are not contiguous in dX: plain 16-byte stores (six layers per backward pass only)
@@ -428,12 +338,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && !(FUSED && p.no_store)) {
+          if (lane == 0) {
             tma_store_2d(&tmapC, stage_base, nbase, mrow0);   // rows >= M and columns >= Ndim are clipped by TMA
             tma_store_commit();
           }
           if (do_stats) stats_narrow(stage_base, lane, rows_valid, cs1[cl], cs2[cl]);
-          if (FUSED && p.no_store) __syncwarp();   // nobody re-stages this buffer while a lane still sums it
           if (L::NBUF == 2) sbuf ^= 1;
         }
       }
@@ -1000,6 +909,13 @@ static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64
   return 0;
 }
 
+// gemm_fused.cu: plain GEMM with TMA-staged residual tile / per-column vectors in the epilogue
+bool gemm_fused_applicable(int M, int C, int Ndim, int ldw, int ldc);
+int gemm_fused_launch(const void* src, const void* wt, void* dst, const void* resid, const void* resid_mask,
+                      const float* colscale, const float* bias, const float* resid_colscale, void* mask_out,
+                      float* col_sum, float* col_sqsum, int M, int C, int Ndim, int ldw, int ldc, int relu, int no_store,
+                      int bwd_reduce, cudaStream_t stream);
+
 // conv_patch.cu
 bool patch_conv_applicable(int H, int W, int C, int Ndim, int KH, int KW, int stride, int pad, int out_fp32,
                            const float* bias, int64_t src_elems);
@@ -1013,11 +929,11 @@ int patch_wgrad_launch(const void* x, const void* dy, float* dw, int Nimg, int H
 
 static int sm_count() { return device_sm_count(); }
 
-template <int BN, int STAGES, bool A_TMA, bool FUSED = false>
+template <int BN, int STAGES, bool A_TMA>
 static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                         const ConvGemmParams& p, int tiles_m, cudaStream_t stream) {
   using L = SmemLayout<BN, STAGES, A_TMA>;
-  auto kern = conv_igemm_kernel<BN, STAGES, A_TMA, FUSED>;
+  auto kern = conv_igemm_kernel<BN, STAGES, A_TMA>;
   static bool attr_set[kMaxDevices] = {};
   const int dev_slot = device_slot();
   if (!attr_set[dev_slot]) {
@@ -1043,20 +959,11 @@ using namespace byol;
 // mode 0 (fprop):  src coord = o*stride - pad + k
 // mode 1 (dgrad):  src coord = (o + pad - k) / stride  (valid only when divisible); here `src` is dY,
 //                  (Hs, Ws) its spatial size and (Ho, Wo) the spatial size of dX.
-struct FusedEpilogue {
-  const float* colscale;
-  const float* resid_colscale;
-  void* mask_out;
-  int no_store;
-  int bwd_reduce;
-};
-
-static int conv_igemm_impl(const void* src, const void* wt, void* dst, const void* resid,
-                           const void* resid_mask, int resid_up, const float* bias, float* col_sum, float* col_sqsum, int Nimg, int Hs, int Ws, int C, int Ho, int Wo,
-                           int Ndim, int KH, int KW, int stride, int pad, int mode, int ldw, int ldc,
-                           int out_fp32, int relu, int force_gather, const FusedEpilogue* fx, cudaStream_t stream) {
-  const bool no_dst = fx != nullptr && (fx->no_store || fx->bwd_reduce);
-  BYOL_CHECK_ARG(src && wt && (dst || no_dst), "byol_conv_igemm: null pointer");
+extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const void* resid,
+                               const void* resid_mask, int resid_up, const float* bias, float* col_sum, float* col_sqsum, int Nimg, int Hs, int Ws, int C, int Ho, int Wo,
+                               int Ndim, int KH, int KW, int stride, int pad, int mode, int ldw, int ldc,
+                               int out_fp32, int relu, int force_gather, cudaStream_t stream) {
+  BYOL_CHECK_ARG(src && wt && dst, "byol_conv_igemm: null pointer");
   BYOL_CHECK_ARG(C % 8 == 0 && C >= 8, "byol_conv_igemm: C=%d must be a multiple of 8", C);
   // bf16 outputs are TMA-stored (16-byte row pitch); fp32 outputs (logits, MLP outputs) may have any width
   BYOL_CHECK_ARG(Ndim > 0 && (Ndim % 8 == 0 || (out_fp32 && resid == nullptr && col_sum == nullptr)),
@@ -1073,7 +980,13 @@ static int conv_igemm_impl(const void* src, const void* wt, void* dst, const voi
   BYOL_CHECK_ARG(!resid_up || (resid != nullptr && resid_mask == nullptr && Ho % 2 == 0 && Wo % 2 == 0 &&
                                !(mode == 1 && stride == 2)),
                  "byol_conv_igemm: resid_up needs resid, even output dims and a non-parity mode");
-  if (fx == nullptr && !force_gather && resid_mask == nullptr && !resid_up && Hs == Ho && Ws == Wo && ldw >= 9 * C &&
+  // 1x1 / stride 1 with a residual tile in the epilogue (conv1 dgrad + the residual-branch gradient): the kernel that
+  // stages the residual by TMA instead of per-lane global loads (3.5x faster at 56x56, tools/time_dgrad_resid.py)
+  if (!force_gather && resid != nullptr && !resid_up && KH == 1 && KW == 1 && stride == 1 && pad == 0 && !out_fp32 &&
+      col_sum == nullptr && gemm_fused_applicable((int)M64, C, Ndim, ldw, ldc))
+    return gemm_fused_launch(src, wt, dst, resid, resid_mask, nullptr, bias, nullptr, nullptr, nullptr, nullptr,
+                             (int)M64, C, Ndim, ldw, ldc, relu, 0, 0, stream);
+  if (!force_gather && resid_mask == nullptr && !resid_up && Hs == Ho && Ws == Wo && ldw >= 9 * C &&
       patch_conv_applicable(Hs, Ws, C, Ndim, KH, KW, stride, pad, out_fp32, bias, (int64_t)Nimg * Hs * Ws * C))
     return patch_conv_launch(src, wt, dst, resid, col_sum, col_sqsum, Nimg, Hs, Ws, C, Ndim, ldw, ldc, mode, relu,
                              sm_count(), stream);
@@ -1102,13 +1015,6 @@ static int conv_igemm_impl(const void* src, const void* wt, void* dst, const voi
   p.num_kb = (p.Kg + BK - 1) / BK;
   p.out_fp32 = out_fp32;
   p.relu = relu;
-  if (fx != nullptr) {
-    p.colscale = fx->colscale;
-    p.resid_colscale = fx->resid_colscale;
-    p.mask_out = (uint8_t*)fx->mask_out;
-    p.no_store = fx->no_store ? 1 : 0;
-    p.bwd_reduce = fx->bwd_reduce ? 1 : 0;
-  }
   p.small_src = ((int64_t)Nimg * Hs * Ws * C < (1ll << 31) - (1ll << 24)) ? 1 : 0;
   const int BN = (Ndim > 64) ? 128 : 64;
   p.tiles_n = (Ndim + BN - 1) / BN;
@@ -1136,7 +1042,7 @@ static int conv_igemm_impl(const void* src, const void* wt, void* dst, const voi
   CUtensorMap ta, tb, tc;
   memset(&ta, 0, sizeof(ta));
   if (make_tmap_2d(&tb, wt, (uint64_t)Ndim, (uint64_t)p.Kg, (uint64_t)ldw, (uint32_t)BN) != 0) return -3;
-  if (!out_fp32 && !no_dst) {
+  if (!out_fp32) {
     if (make_tmap_2d(&tc, dst, (uint64_t)p.M, (uint64_t)Ndim, (uint64_t)ldc, 32u, 32u) != 0) return -3;
   } else {
     tc = tb;
@@ -1146,52 +1052,12 @@ static int conv_igemm_impl(const void* src, const void* wt, void* dst, const voi
   } else {
     ta = tb;
   }
-  if (fx != nullptr) {
-    // the fused BatchNorm epilogues exist for the TMA-operand GEMM only (1x1 / stride 1 convolutions, linears)
-    BYOL_CHECK_ARG(a_tma && !out_fp32 && !p.parity && !resid_up,
-                   "byol_conv_igemm_fused: needs a plain bf16 GEMM (1x1, stride 1, pad 0)");
-    BYOL_CHECK_ARG(!fx->bwd_reduce || (resid != nullptr && col_sum != nullptr && col_sqsum != nullptr),
-                   "byol_conv_igemm_fused: bwd_reduce needs the gradient tile (resid) and both sum buffers");
-    return BN == 128 ? launch_igemm<128, 3, true, true>(ta, tb, tc, p, tiles_m, stream)
-                     : launch_igemm<64, 3, true, true>(ta, tb, tc, p, tiles_m, stream);
-  }
   if (BN == 128) {
     return a_tma ? launch_igemm<128, 3, true>(ta, tb, tc, p, tiles_m, stream)
                  : launch_igemm<128, 3, false>(ta, tb, tc, p, tiles_m, stream);
   }
   return a_tma ? launch_igemm<64, 3, true>(ta, tb, tc, p, tiles_m, stream)
                : launch_igemm<64, 4, false>(ta, tb, tc, p, tiles_m, stream);
-}
-
-extern "C" int byol_conv_igemm(const void* src, const void* wt, void* dst, const void* resid,
-                               const void* resid_mask, int resid_up, const float* bias, float* col_sum, float* col_sqsum, int Nimg, int Hs, int Ws, int C, int Ho, int Wo,
-                               int Ndim, int KH, int KW, int stride, int pad, int mode, int ldw, int ldc,
-                               int out_fp32, int relu, int force_gather, cudaStream_t stream) {
-  return conv_igemm_impl(src, wt, dst, resid, resid_mask, resid_up, bias, col_sum, col_sqsum, Nimg, Hs, Ws, C, Ho, Wo,
-                         Ndim, KH, KW, stride, pad, mode, ldw, ldc, out_fp32, relu, force_gather, nullptr, stream);
-}
-
-// 1x1 / stride-1 convolution (plain GEMM: out[M, Ndim] = src[M, C] x wt[Ndim, C]^T) with a fused BatchNorm epilogue:
-//     t   = acc * colscale[n] + bias[n]
-//     out = act( t + resid_colscale[n] * (resid_mask ? resid : 0) )          -> dst (bf16), mask_out = bits (out > 0)
-// no_store = 1  : nothing is written; only the column statistics (col_sum / col_sqsum of the bf16-rounded acc) are
-//                 produced — pass 1 of "statistics pass + recompute", which never materialises the raw conv output
-// bwd_reduce = 1: nothing is written; with dz = (resid_mask ? resid : 0): col_sum += sum_m dz, col_sqsum += sum_m dz*t
-//                 (t = xhat when colscale = invstd and bias = -mean*invstd): the BatchNorm-backward sums of a
-//                 recomputed conv output
-extern "C" int byol_conv_igemm_fused(const void* src, const void* wt, void* dst, const void* resid,
-                                     const void* resid_mask, const float* colscale, const float* bias,
-                                     const float* resid_colscale, void* mask_out, float* col_sum, float* col_sqsum,
-                                     int M, int C, int Ndim, int ldw, int ldc, int relu, int no_store, int bwd_reduce,
-                                     cudaStream_t stream) {
-  FusedEpilogue fx;
-  fx.colscale = colscale;
-  fx.resid_colscale = resid_colscale;
-  fx.mask_out = mask_out;
-  fx.no_store = no_store;
-  fx.bwd_reduce = bwd_reduce;
-  return conv_igemm_impl(src, wt, dst, resid, resid_mask, 0, bias, col_sum, col_sqsum, M, 1, 1, C, 1, 1, Ndim, 1, 1, 1,
-                         0, 0, ldw, ldc, 0, relu, 0, &fx, stream);
 }
 
 template <int BN, bool B_TMA>

@@ -272,7 +272,7 @@ def test_linear(cuda, case):
     assert_close("linear_wgrad[%s]" % name, dw, refdw, atol=2e-3 * float(refdw.abs().max()), rtol=0)
 
 
-@pytest.mark.parametrize("m,k,n", [(5000, 64, 256), (777, 512, 2048), (4096, 256, 64), (300, 128, 136)])
+@pytest.mark.parametrize("m,k,n", [(5000, 64, 256), (777, 512, 2048), (4096, 256, 128), (300, 128, 136)])
 def test_gemm_fused_bn_epilogues(cuda, m, k, n):
     """byol_conv_igemm_fused: the 1x1 convolution whose BatchNorm (+ residual + ReLU) lives in the epilogue
     (statistics pass / apply pass) and whose BatchNorm backward recomputes the conv output (reduce / apply)."""
