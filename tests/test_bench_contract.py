@@ -34,18 +34,23 @@ def test_reference_arm_runs_on_cpu():
 
 
 def test_committed_gpu_bench_lines():
-    for name, n in (("bench_r01_n1_b512.json", 1), ("bench_r01_n2_current.json", 2), ("bench_r01_n8_current.json", 8)):
-        line = json.load(open(os.path.join(ROOT, "profiles", name)))
+    for name, n in (("bench_r02_n1_b512.json", 1), ("scale_r02_n2.json", 2), ("scale_r02_n4.json", 4),
+                    ("scale_r02_n8.json", 8)):
+        line = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
         assert line["n_gpus"] == n and line["dtype"] == "bf16" and line["steps"] >= 1 and line["warmup"] >= 3
         if n == 1:
             _check_common(line)
-        else:   # the N > 1 lines were taken with --no-cpu-baseline
+            assert line["cpu_baseline"]["kind"] in ("reference", "port")
+        else:   # cpu_baseline is reported on rank 0 at N = 1 only
             assert (BASE_KEYS - {"cpu_baseline"}) <= set(line)
-        assert line["gpu_launches"] > 0
+        assert line["gpu_launches"] > 0 and line["config"]["cuda_graphs"] is True
+        assert line["host_enqueue_ms_per_step"] < 10.0          # the step is replayed from CUDA graphs
         assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
         assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(line["clocks"]["reasons"]))
         roof = line["roofline"]
         assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(roof)
         assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
+        if n == 1:
+            assert roof["traffic"] > 1e11 and 0.3 < roof["hbm_view"]["frac"] < 1.0
         # e2e moves the step's inputs through pinned host memory: two fp32 views per image
         assert line["e2e"]["h2d_bytes_per_step"] >= 2 * 3 * 224 * 224 * 4 * 512 and line["e2e"]["d2h_bytes_per_step"] > 0
