@@ -82,6 +82,11 @@ _SIGNATURES = {
                           c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
     "byol_maxpool_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "byol_avgpool_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "byol_mlp_fused_supported": [c_int, c_int, c_int, c_int],
+    "byol_mlp_fused_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_void_p, c_float, c_float, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                           c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int64, c_void_p,
+                           c_void_p],
     "byol_xchg_layout": [c_void_p, c_void_p, c_void_p],
     "byol_xchg_sum": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p],
     "byol_abi_version": [],

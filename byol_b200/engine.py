@@ -155,6 +155,9 @@ class Engine(object):
         # elementwise kernels at ~85 %.  It saves 7-14 GB of activations per 512 images; BYOL_B200_FUSE3=1 enables it.
         self.fuse3 = os.environ.get("BYOL_B200_FUSE3", "0") == "1"
         self.fuse3_max_planes = int(os.environ.get("BYOL_B200_FUSE3_MAX_PLANES", "128"))
+        # projector / predictor forward as one cooperative kernel per lane (csrc/mlp_fused.cu); =0: four launches
+        self.fused_mlp = os.environ.get("BYOL_B200_FUSED_MLP", "1") != "0"
+        self._mlp_bar = None
 
     # ------------------------------------------------------------------------------------------
     # flat buffers
@@ -469,7 +472,49 @@ class Engine(object):
                     "cd": cd[i] if cd is not None else None, "out": outs[i]})
         return outs
 
+    def _mlp_fused_ok(self, mlp, b):
+        l1, l2 = mlp
+        if not self.fused_mlp or (self.sync and comm.uses_nccl_for_statistics(self.device)):
+            return False            # the in-kernel statistics exchange needs the peer-memory channel
+        return l1.bn is not None and l1.b_off >= 0 and l2.b_off >= 0 and \
+            ops.mlp_fused_supported(b, l1.cin, l1.cout, l2.cout)
+
+    def _mlp_fwd_fused(self, mlp, xs, lanes, train, key):
+        """Linear -> BatchNorm1d -> ReLU -> Linear as ONE cooperative kernel per lane (csrc/mlp_fused.cu): the hidden
+        activation stays in TMEM / shared memory between the two GEMMs; the BatchNorm statistics cross the grid
+        (and, under SyncBatchNorm, the ranks) inside the kernel."""
+        l1, l2 = mlp
+        H, bn = l1.cout, l1.bn
+        ch = self._group_order
+        if self._mlp_bar is None:
+            self._mlp_bar = torch.zeros((comm.NUM_CHANNELS, 2), dtype=torch.int32, device=self.device)
+        peer, world = None, 1
+        if train and self.sync and self.world() > 1:
+            peer, world = comm.peer_exchange(self.device)[ch], self.world()
+        fin = self._fin_events
+        if train and fin is not None and ch == 1:
+            torch.cuda.current_stream().wait_event(fin[l1.idx])      # running statistics: online pair first
+        outs_f, outs_b = [], []
+        for i, (flat, wset, saved) in enumerate(lanes):
+            stats = self._zpool.take(2 * H) if train else None
+            coeffs = self._cpool.take(4 * H).view(4, H)
+            o, h, a = ops.mlp_fused_fwd(
+                xs[i], wset.wf[l1.idx], flat[l1.b_off:l1.b_off + H], flat[l1.g_off:l1.g_off + H],
+                flat[l1.beta_off:l1.beta_off + H], wset.wf[l2.idx], flat[l2.b_off:l2.b_off + l2.cout], stats,
+                bn.running_mean, bn.running_var, bn.momentum, bn.eps, xs[i].shape[0] * world, coeffs, self._mlp_bar[ch],
+                train, saved is not None, peer)
+            outs_f.append(o)
+            outs_b.append(ops.cast_bf16(o))
+            if saved is not None:
+                saved[key] = {"x": xs[i], "h": h, "c": coeffs, "a": a}
+        if train and fin is not None and ch == 0:
+            fin[l1.idx] = torch.cuda.Event()
+            fin[l1.idx].record(torch.cuda.current_stream())
+        return outs_f, outs_b
+
     def _mlp_fwd(self, mlp, xs, lanes, train, key):
+        if self._mlp_fused_ok(mlp, xs[0].shape[0]):
+            return self._mlp_fwd_fused(mlp, xs, lanes, train, key)
         l1, l2 = mlp
         L = len(lanes)
         h, c = self._conv_bn(l1, xs, lanes, train)
@@ -989,7 +1034,7 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------
     def graph_key(self, a1):
         return (tuple(a1.shape), self.world(), bool(self.sync), self.theta.data_ptr(), self.multi_stream,
-                self.overlap_wgrad, self.T, self.fuse3, self.fuse3_max_planes)
+                self.overlap_wgrad, self.T, self.fuse3, self.fuse3_max_planes, self.fused_mlp)
 
     def prep_step(self, mean, training):
         """All weight layouts one forward (+ backward) needs, from the fp32 masters."""

@@ -228,6 +228,34 @@ def gemm_fused(x2d, w_f, out=None, colscale=None, bias=None, resid=None, resid_m
     return out
 
 
+def mlp_fused_supported(b, k1, h, o):
+    return bool(lib.byol_mlp_fused_supported(b, k1, h, o))
+
+
+def mlp_fused_fwd(x2d, w1, b1, gamma, beta, w2, b2, stats, running_mean, running_var, momentum, eps, count, coeffs,
+                  grid_bar, train, save, peer=None):
+    """Linear -> BatchNorm1d -> ReLU -> Linear of one lane in ONE cooperative kernel (csrc/mlp_fused.cu).
+    stats: zeroed fp32 [2H] (train); coeffs: fp32 [4, H] out; grid_bar: persistent zeroed int32 [2] (one per stream);
+    peer: comm.PeerExchange of this stream's channel under SyncBatchNorm (world > 1), else None.
+    Returns (out fp32 [B, O], h bf16 [B, H] | None, a bf16 [B, H] | None)."""
+    _chk(x2d, BF16, "x"); _chk(w1, BF16, "w1"); _chk(w2, BF16, "w2"); _chk(stats, F32, "stats")
+    b, k1 = x2d.shape
+    h, ldw1 = w1.shape
+    o, ldw2 = w2.shape
+    dev = x2d.device
+    out = torch.zeros((b, o), dtype=F32, device=dev)
+    hs = torch.empty((b, h), dtype=BF16, device=dev) if save else None
+    as_ = torch.empty((b, h), dtype=BF16, device=dev) if save else None
+    pp, world, rank, cap, ctr = 0, 1, 0, 0, 0
+    if peer is not None:
+        pp, world, rank, cap, ctr = peer.ptrs, peer.world, peer.rank, peer.cap_bytes, peer.counter.data_ptr()
+    check(lib.byol_mlp_fused_fwd(_ptr(x2d), _ptr(w1), _ptr(b1), _ptr(gamma), _ptr(beta), _ptr(w2), _ptr(b2), _ptr(stats),
+                                 _ptr(running_mean), _ptr(running_var), float(momentum), float(eps), float(count),
+                                 _ptr(coeffs), _ptr(out), _ptr(hs), _ptr(as_), _ptr(grid_bar), b, k1, h, o, ldw1, ldw2,
+                                 int(train), pp, world, rank, cap, ctr, _stream()), "byol_mlp_fused_fwd")
+    return out, hs, as_
+
+
 def bn_bwd_prep(mean, invstd, out=None):
     c = mean.numel()
     if out is None:

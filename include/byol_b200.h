@@ -190,6 +190,19 @@ int byol_maxpool_f32(const float* x, float* y, void* idx, int N, int H, int W, i
                      byol_stream_t stream);
 int byol_avgpool_f32(const float* x, float* y, int N, int HW, int C, byol_stream_t stream);
 
+/* ---- projector / predictor MLP forward as ONE cooperative kernel (main.py:194-205, 238-239):
+ *      Linear -> BatchNorm1d (batch statistics, grid barrier, optional cross-rank exchange) -> ReLU -> Linear.
+ *      x [B, K1] bf16, w1 [H, ldw1], w2 [O, ldw2] bf16 (fprop layouts); stats [2H] and out [B, O] fp32 ZEROED by the
+ *      caller; coeffs [4, H]; h_save / a_save optional bf16 [B, H] (for the backward pass); grid_bar: 2 zeroed uint32.
+ *      See csrc/mlp_fused.cu. ---- */
+int byol_mlp_fused_supported(int B, int K1, int H, int O);
+int byol_mlp_fused_fwd(const void* x, const void* w1, const float* b1, const float* gamma, const float* beta,
+                       const void* w2, const float* b2, float* stats, float* running_mean, float* running_var,
+                       float momentum, float eps, double count, float* coeffs, float* out, void* h_save, void* a_save,
+                       void* grid_bar, int B, int K1, int H, int O, int ldw1, int ldw2, int train,
+                       const uint64_t* peer_ptrs, int world, int rank, int64_t cap_bytes, void* counter,
+                       byol_stream_t stream);
+
 /* ---- SyncBatchNorm statistic exchange over NVLink peer memory (main.py:433; replaces the per-layer all_gather /
  *      all_reduce of torch/nn/modules/_functions.py:49-74,158-159): one single-CTA kernel per exchange — publish into
  *      this rank's symmetric buffer, flag every peer, wait, add all peers' values in rank order.  See csrc/xchg.cu. */

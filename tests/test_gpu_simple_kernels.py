@@ -371,3 +371,51 @@ def test_cross_entropy_topk(cuda, rows, classes, tile):
     # deterministic: the row reduction has a fixed order
     loss2, _, _ = cross_entropy_topk(ld.detach(), labels.to(cuda))
     assert torch.equal(loss2, loss.detach())
+
+
+@pytest.mark.parametrize("b,k1,h,o", [(512, 2048, 4096, 256), (24, 256, 4096, 256), (200, 512, 256, 64)])
+def test_mlp_fused_forward(cuda, b, k1, h, o):
+    """main.py:194-205: Linear -> BatchNorm1d -> ReLU -> Linear as ONE cooperative kernel (train and eval mode),
+    against fp32 torch on the bf16-rounded operands (the hidden activation is rounded to bf16 between the GEMMs, as
+    in the unfused kernels)."""
+    from byol_b200 import ops
+    if not ops.mlp_fused_supported(b, k1, h, o):
+        pytest.skip("shape not supported by the cooperative kernel on this device")
+    g = torch.Generator().manual_seed(b + h)
+    x = R.bf16_round(torch.randn(b, k1, generator=g))
+    w1 = R.bf16_round(torch.randn(h, k1, generator=g) / k1 ** 0.5)
+    w2 = R.bf16_round(torch.randn(o, h, generator=g) / h ** 0.5)
+    b1, b2 = torch.randn(h, generator=g) * 0.1, torch.randn(o, generator=g) * 0.1
+    gamma, beta = torch.rand(h, generator=g) + 0.5, torch.randn(h, generator=g) * 0.1
+    dev = lambda t, dt=None: t.to(cuda, dt) if dt is not None else t.to(cuda)
+    hid = x.double() @ w1.double().t() + b1.double()
+    mean, var = hid.mean(0), hid.var(0, unbiased=False)
+    a = torch.relu((hid - mean) / torch.sqrt(var + 1e-5) * gamma.double() + beta.double())
+    out_ref = R.bf16_round(a.float()).double() @ w2.double().t() + b2.double()
+    stats = torch.zeros(2 * h, device=cuda)
+    rm, rv = torch.zeros(h, device=cuda), torch.ones(h, device=cuda)
+    coeffs = torch.empty(4, h, device=cuda)
+    bar = torch.zeros(2, dtype=torch.int32, device=cuda)
+    for rep in range(2):          # twice: the grid barrier state must be reusable
+        stats.zero_()
+        out, hs, as_ = ops.mlp_fused_fwd(dev(x, BF), dev(w1, BF), dev(b1), dev(gamma), dev(beta), dev(w2, BF), dev(b2),
+                                         stats, rm, rv, 0.1, 1e-5, b, coeffs, bar, True, True)
+    torch.cuda.synchronize()
+    assert_close("mlp_fused_mean", coeffs[2], mean.float(), atol=2e-4, rtol=1e-4)
+    assert_close("mlp_fused_invstd", coeffs[3], (1 / torch.sqrt(var + 1e-5)).float(), atol=0, rtol=2e-4)
+    assert_close("mlp_fused_h", hs, hid.float(), atol=2e-2, rtol=1e-2)
+    assert_close("mlp_fused_a", as_, a.float(), atol=3e-2, rtol=1e-2)
+    assert_close("mlp_fused_out", out, out_ref.float(), atol=3e-3 * float(out_ref.abs().max()), rtol=1e-2)
+    unb = var * b / (b - 1)
+    rm_ref = 0.1 * mean + 0.9 * (0.1 * mean)                   # two updates from (0, 1)
+    rv_ref = 0.9 * (0.9 * 1 + 0.1 * unb) + 0.1 * unb
+    assert_close("mlp_fused_running_mean", rm, rm_ref.float(), atol=2e-4, rtol=1e-4)
+    assert_close("mlp_fused_running_var", rv, rv_ref.float(), atol=1e-5, rtol=2e-4)
+    # eval mode: running statistics, nothing saved
+    out_e, hs_e, _ = ops.mlp_fused_fwd(dev(x, BF), dev(w1, BF), dev(b1), dev(gamma), dev(beta), dev(w2, BF), dev(b2),
+                                       None, rm, rv, 0.1, 1e-5, b, coeffs, bar, False, False)
+    torch.cuda.synchronize()
+    ae = torch.relu((hid - rm.cpu().double()) / torch.sqrt(rv.cpu().double() + 1e-5) * gamma.double() + beta.double())
+    oe = R.bf16_round(ae.float()).double() @ w2.double().t() + b2.double()
+    assert hs_e is None
+    assert_close("mlp_fused_out_eval", out_e, oe.float(), atol=3e-3 * float(oe.abs().max()), rtol=1e-2)
