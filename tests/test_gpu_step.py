@@ -271,7 +271,7 @@ def test_cuda_graph_replay_matches_eager(cuda):
     print("losses eager %s graph %s" % (le, lg))
     # (fp32 atomics make two executions of one step agree to ~1e-4 only, and three LARS steps at lr 0.2 amplify
     # that: the tolerances are those of eager-vs-eager, see tests/test_gpu_checkpoint.py)
-    assert np.allclose(le[:2], lg[:2], rtol=5e-4) and np.allclose(le, lg, rtol=5e-3)
+    assert np.allclose(le[:2], lg[:2], rtol=2e-3) and np.allclose(le, lg, rtol=1e-2)
     assert res["eager"][3] == res["graph"][3] == 16 and res["eager"][4] == res["graph"][4] == 5
     assert torch.allclose(res["eager"][5], res["graph"][5], rtol=2e-2, atol=2e-3)
     upd_e, upd_g = res["eager"][1], res["graph"][1]
