@@ -630,8 +630,19 @@ class Engine(object):
             reps_b.append(yb)
             if lanes[i][2] is not None:
                 lanes[i][2]["final_shape"] = (n, h, w, c)
+        # Under SyncBatchNorm the fused MLP kernels are cooperative (most of the GPU each) AND wait for their peer
+        # ranks: two of them from different streams must never be schedulable in different orders on different ranks
+        # (rank X resident with stream A's kernel, rank Y with stream B's -> circular wait).  So the second lane pair
+        # enters its MLP section only after the first pair has left it: A-head, A-pred, B-head, B-pred everywhere.
+        gate = train and self.sync and self.world() > 1 and self._fin_events is not None and \
+            self._mlp_fused_ok(self.mlps[0], reps_b[0].shape[0])
+        if gate and self._group_order == 1:
+            torch.cuda.current_stream().wait_event(self._fin_events["mlp_gate"])
         proj_f, proj_b = self._mlp_fwd(self.mlps[0], reps_b, lanes, train, "head")
         pred_f, _ = self._mlp_fwd(self.mlps[1], proj_b, lanes, train, "pred")
+        if gate and self._group_order == 0:
+            self._fin_events["mlp_gate"] = torch.cuda.Event()
+            self._fin_events["mlp_gate"].record(torch.cuda.current_stream())
         return [(reps_f[i], proj_f[i], pred_f[i]) for i in range(L)], reps_b
 
     # ------------------------------------------------------------------------------------------
