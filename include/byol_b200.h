@@ -210,6 +210,16 @@ int byol_xchg_layout(int* slots, int* max_world, int* flag_bytes);
 int byol_xchg_sum(void* vals, void* local_copy, int n, int is_f64, const uint64_t* peer_ptrs /* host, [world] */,
                   int world, int rank, int64_t cap_bytes, void* counter /* device uint32 */, byol_stream_t stream);
 
+/* ---- on-device two-view augmentation (main.py:386-397: RandomResizedCrop, flip, ColorJitter p = 0.8, grayscale
+ *      p = 0.2, Gaussian blur p = 0.5) for decoded fp32 NCHW images resident in HBM.  params: fp32 [2, N, 16] records
+ *      (view-major; byol_augment_record_floats() floats each: crop top / left / h / w, flip, jitter on, op order x 4,
+ *      brightness, contrast, saturation, hue, gray on, blur sigma).  See csrc/augment.cu. ---- */
+int byol_augment_record_floats(void);
+int byol_augment_params(float* params, int N, int Hs, int Ws, uint64_t seed, uint64_t step, float strength,
+                        float p_flip, float p_jitter, float p_gray, float p_blur, byol_stream_t stream);
+int byol_augment_apply(const float* src, const float* params, float* out /* [2, N, 3, R, R] */, float* tmp,
+                       double* gray_sum /* [2N] */, int N, int Hs, int Ws, int R, int ksize, byol_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
