@@ -75,7 +75,14 @@ def test_augment_parameter_distribution(cuda):
     area = ch * cw / (hs * ws)
     ratio = cw / ch
     assert area.min() > 0.07 and area.max() <= 1.0 and 0.70 < ratio.min() and ratio.max() < 1.40
-    assert abs(area.mean() - 0.54) < 0.06                               # U(0.08, 1) minus the rejected draws
+    # against torchvision's own sampler (RandomResizedCrop.get_params: 10 attempts, then a centre crop)
+    import torchvision.transforms as T
+    torch.manual_seed(0)
+    dummy = torch.zeros(3, hs, ws)
+    ref = np.array([T.RandomResizedCrop.get_params(dummy, (0.08, 1.0), (3. / 4., 4. / 3.)) for _ in range(4000)])
+    ref_area = ref[:, 2] * ref[:, 3] / (hs * ws)
+    assert abs(area.mean() - ref_area.mean()) < 0.02 and abs(area.std() - ref_area.std()) < 0.02
+    assert abs(np.log(ratio).std() - np.log(ref[:, 3] / ref[:, 2]).std()) < 0.02
     for col, prob in ((4, 0.5), (5, 0.8), (14, 0.2)):
         assert abs((p[:, col] != 0).mean() - prob) < 0.02, col
     assert abs((p[:, 15] > 0).mean() - 0.5) < 0.02
