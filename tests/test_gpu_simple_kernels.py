@@ -419,3 +419,44 @@ def test_mlp_fused_forward(cuda, b, k1, h, o):
     oe = R.bf16_round(ae.float()).double() @ w2.double().t() + b2.double()
     assert hs_e is None
     assert_close("mlp_fused_out_eval", out_e, oe.float(), atol=3e-3 * float(oe.abs().max()), rtol=1e-2)
+
+
+def test_maxpool_bwd_generic_and_fast_paths_agree(cuda):
+    """The 2x2-block kernel (k3 s2 p1, even sizes) and the generic window-search kernel against autograd."""
+    from byol_b200 import ops
+    g = torch.Generator().manual_seed(66)
+    for h in (12, 11, 56):          # 11 -> generic kernel (H != 2 Ho)
+        x = R.bf16_round(torch.relu(torch.randn(3, h, h, 64, generator=g)))
+        y, idx = ops.maxpool_fwd(x.to(cuda, BF))
+        ho = y.shape[1]
+        dy = R.bf16_round(torch.randn(3, ho, ho, 64, generator=g))
+        dx = ops.maxpool_bwd(dy.to(cuda, BF), idx, h, h)
+        torch.cuda.synchronize()
+        assert_close("maxpool_bwd_%d" % h, dx, R.maxpool_bwd_ref(x, dy), atol=2e-2, rtol=1e-2)
+
+
+def test_prep_weights_multi_matches_single(cuda):
+    """One-launch conversion of a whole parameter set (tiled transpose) == the per-tensor kernel, for 1x1, 3x3 and
+    non-multiple-of-32 shapes, fprop and dgrad layouts."""
+    from byol_b200 import ops
+    g = torch.Generator().manual_seed(67)
+    shapes = [(64, 64, 1), (128, 64, 3), (72, 40, 3), (1000, 2048, 1), (256, 1024, 1)]
+    ws = [torch.randn(co, ci, k, k, generator=g) for co, ci, k in shapes]
+    flat = torch.cat([w.reshape(-1) for w in ws]).to(cuda)
+    nf = sum(w.numel() for w in ws)
+    pool_f = torch.zeros(nf, dtype=BF, device=cuda)
+    pool_d = torch.zeros(nf, dtype=BF, device=cuda)
+    rows, off = [], 0
+    for (co, ci, k), w in zip(shapes, ws):
+        rows.append([off, off, off, co, ci, ci, k * k, 0])
+        off += w.numel()
+    desc = torch.tensor(rows, dtype=torch.int64, device=cuda)
+    ops.prep_weights_multi(flat, pool_f, pool_d, desc)
+    torch.cuda.synchronize()
+    off = 0
+    for (co, ci, k), w in zip(shapes, ws):
+        wf, wd = ops.prep_weight(w.to(cuda))
+        n = w.numel()
+        assert torch.equal(pool_f[off:off + n].view_as(wf), wf), (co, ci, k)
+        assert torch.equal(pool_d[off:off + n].view_as(wd), wd), (co, ci, k)
+        off += n
