@@ -263,6 +263,52 @@ __global__ void bn_relu_maxpool_fwd_kernel(const bf16* __restrict__ x, const flo
   }
 }
 
+// Same without the argmax (target lanes keep nothing for a backward pass): candidates are packed to bf16x2 right
+// after the normalisation and reduced with packed max — half the instructions of the index-tracking kernel.
+__global__ void __launch_bounds__(256)
+bn_relu_maxpool_fwd_noidx_kernel(const bf16* __restrict__ x, const float* __restrict__ scale,
+                                 const float* __restrict__ shift, bf16* __restrict__ y, int N, int H, int W, int C,
+                                 int Ho, int Wo, int k, int s, int p) {
+  const int groups = C >> 3;
+  const int64_t total = (int64_t)N * Ho * Wo * groups;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    int64_t t = i / groups;
+    const int ow = (int)(t % Wo); t /= Wo;
+    const int oh = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sc[e] = __ldg(scale + g * 8 + e); sh[e] = __ldg(shift + g * 8 + e); }
+    __nv_bfloat162 best[4];
+    bool any = false;
+    for (int kh = 0; kh < k; ++kh) {
+      const int ih = oh * s - p + kh;
+      if (ih < 0 || ih >= H) continue;
+      for (int kw = 0; kw < k; ++kw) {
+        const int iw = ow * s - p + kw;
+        if (iw < 0 || iw >= W) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)n * H + ih) * W + iw) * C + g * 8));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(h[e]);
+          const __nv_bfloat162 c2 = __floats2bfloat162_rn(fmaxf(f.x * sc[2 * e] + sh[2 * e], 0.f),
+                                                          fmaxf(f.y * sc[2 * e + 1] + sh[2 * e + 1], 0.f));
+          best[e] = any ? __hmax2_nan(best[e], c2) : c2;
+        }
+        any = true;
+      }
+    }
+    uint4 q;
+    q.x = *reinterpret_cast<uint32_t*>(&best[0]);
+    q.y = *reinterpret_cast<uint32_t*>(&best[1]);
+    q.z = *reinterpret_cast<uint32_t*>(&best[2]);
+    q.w = *reinterpret_cast<uint32_t*>(&best[3]);
+    reinterpret_cast<uint4*>(y)[i] = q;
+  }
+}
+
 // dx[n, ih, iw, c] = sum over output windows (oh, ow) containing (ih, iw) whose saved argmax is this position
 __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ idx,
                                    bf16* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo, int k, int s,
@@ -547,6 +593,11 @@ extern "C" int byol_bn_relu_maxpool_fwd(const void* x, const float* scale, const
   BYOL_CHECK_ARG(x && scale && shift && y && C % 8 == 0 && k * k <= 255, "byol_bn_relu_maxpool_fwd: bad args");
   const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
   const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+  if (idx == nullptr) {
+    bn_relu_maxpool_fwd_noidx_kernel<<<grid_for((int64_t)N * Ho * Wo * (C / 8), 256), 256, 0, stream>>>(
+        (const bf16*)x, scale, shift, (bf16*)y, N, H, W, C, Ho, Wo, k, s, p);
+    return check_launch("bn_relu_maxpool_fwd_noidx_kernel");
+  }
   bn_relu_maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const bf16*)x, scale, shift, (bf16*)y,
                                                                       (uint8_t*)idx, N, H, W, C, Ho, Wo, k, s, p);
   return check_launch("bn_relu_maxpool_fwd_kernel");

@@ -182,8 +182,10 @@ def test_fused_stem_pool_is_bit_identical(cuda):
     a = ops.bn_apply(x.view(-1, 64), sc, sh, relu=True).view(3, 18, 22, 64)
     y1, i1 = ops.maxpool_fwd(a)
     y2, i2 = ops.bn_relu_maxpool_fwd(x, sc, sh)
+    y3, i3 = ops.bn_relu_maxpool_fwd(x, sc, sh, want_idx=False)     # target lanes: packed-max kernel without argmax
     torch.cuda.synchronize()
     assert torch.equal(y1, y2) and torch.equal(i1, i2)
+    assert i3 is None and torch.equal(y1, y3)
 
 
 def test_subsample2(cuda):
