@@ -51,7 +51,8 @@ _SIGNATURES = {
     "byol_nchw_to_nhwc8": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "byol_prep_weight": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "byol_prep_weight_fold": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
-    "byol_prep_weights_multi": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "byol_prep_unit_blocks": [c_int, c_int, c_int, c_int, c_int],
+    "byol_prep_weights_multi": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "byol_subsample2": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "byol_cast_f32_bf16": [c_void_p, c_void_p, c_int64, c_void_p],
     "byol_cast_f32_bf16_2d": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],

@@ -102,9 +102,31 @@ __global__ void prep_weight_fold_kernel(const float* __restrict__ w, bf16* __res
 
 // All conv / linear weights of one parameter set in ONE launch.  desc[u] = {src_off, dstf_off, dstd_off (-1: none),
 // Cout, Cin, Cpad, taps, fold(KH,KW packed as KH*16+KW or 0)} (int64 each); blockIdx.y = unit, grid-stride in x.
+__host__ __device__ inline int prep_unit_blocks(int Cout, int Cin, int Cpad, int taps, int fold) {
+  if (!fold && taps <= 9 && Cpad == Cin) return ((Cin + 31) / 32) * ((Cout + 31) / 32);      // 32 x 32 tiles
+  const int64_t total = fold ? (int64_t)Cout * (fold >> 4) * 64 : (int64_t)Cout * taps * Cpad;
+  return (int)((total + 8191) / 8192);
+}
+
 __global__ void prep_weights_multi_kernel(const float* __restrict__ flat, bf16* __restrict__ pool_f,
-                                          bf16* __restrict__ pool_d, const int64_t* __restrict__ desc) {
-  const int64_t* d = desc + (int64_t)blockIdx.y * 8;
+                                          bf16* __restrict__ pool_d, const int64_t* __restrict__ desc, int num_units) {
+  // Work is balanced over the units: every unit owns prep_unit_blocks() consecutive blocks of the 1-D grid (a
+  // [2048 x 4096] Linear needs 8192 tiles, a BatchNorm-sized conv a handful), found by a scan over the <= ~60 units.
+  __shared__ int s_unit, s_local, s_nb;
+  if (threadIdx.x == 0) {
+    int rem = (int)blockIdx.x, u = 0, nb = 0;
+    for (; u < num_units; ++u) {
+      const int64_t* du = desc + (int64_t)u * 8;
+      nb = prep_unit_blocks((int)du[3], (int)du[4], (int)du[5], (int)du[6], (int)du[7]);
+      if (rem < nb) break;
+      rem -= nb;
+    }
+    s_unit = u; s_local = rem; s_nb = nb;
+  }
+  __syncthreads();
+  if (s_unit >= num_units) return;
+  const int bx = s_local, nbx = s_nb;          // this block's index / block count inside its unit
+  const int64_t* d = desc + (int64_t)s_unit * 8;
   const float* w = flat + d[0];
   bf16* wf = pool_f + d[1];
   bf16* wd = d[2] >= 0 ? pool_d + d[2] : nullptr;
@@ -112,7 +134,7 @@ __global__ void prep_weights_multi_kernel(const float* __restrict__ flat, bf16* 
   if (fold) {
     const int KH = fold >> 4, KW = fold & 15;
     const int64_t total = (int64_t)Cout * KH * 64;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = bx * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)nbx * blockDim.x) {
       const int c = (int)(i & 7);
       const int kw = (int)((i >> 3) & 7);
       const int64_t t = i >> 6;
@@ -125,7 +147,7 @@ __global__ void prep_weights_multi_kernel(const float* __restrict__ flat, bf16* 
     return;
   }
   const int64_t total = (int64_t)Cout * taps * Cpad;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = bx * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)nbx * blockDim.x) {
     const int c = (int)(i % Cpad);
     const int64_t t = i / Cpad;
     const int tap = (int)(t % taps);
@@ -538,11 +560,15 @@ extern "C" int byol_prep_weight_fold(const float* w, void* w_fprop, int Cout, in
 }
 
 // desc: device array [num_units][8] int64 (see prep_weights_multi_kernel); pool_d may be null if no entry needs it
+extern "C" int byol_prep_unit_blocks(int Cout, int Cin, int Cpad, int taps, int fold) {
+  return prep_unit_blocks(Cout, Cin, Cpad, taps, fold);
+}
+
 extern "C" int byol_prep_weights_multi(const float* flat, void* pool_f, void* pool_d, const int64_t* desc,
-                                       int num_units, cudaStream_t stream) {
-  BYOL_CHECK_ARG(flat && pool_f && desc && num_units > 0, "byol_prep_weights_multi: bad args");
-  dim3 grid(128, num_units);   // blocks beyond a small unit's size exit at once; the largest (8M elements) need them   // blocks beyond a small unit's size exit at once; the largest (8M elements) need them
-  prep_weights_multi_kernel<<<grid, 256, 0, stream>>>(flat, (bf16*)pool_f, (bf16*)pool_d, desc);
+                                       int num_units, int num_blocks, cudaStream_t stream) {
+  BYOL_CHECK_ARG(flat && pool_f && desc && num_units > 0 && num_blocks > 0, "byol_prep_weights_multi: bad args");
+  // num_blocks = sum over units of byol_prep_unit_blocks(...) (the host knows the shapes; desc lives on the device)
+  prep_weights_multi_kernel<<<num_blocks, 256, 0, stream>>>(flat, (bf16*)pool_f, (bf16*)pool_d, desc, num_units);
   return check_launch("prep_weights_multi_kernel");
 }
 

@@ -79,6 +79,7 @@ class _Weights(object):
             rows_d.append(base)
         self.desc_with_dgrad = torch.tensor(rows_d, dtype=torch.int64, device=device)
         self.desc_fprop_only = torch.tensor(rows_n, dtype=torch.int64, device=device)
+        self.prep_blocks = ops.prep_blocks(rows_n)      # same shapes in both tables
         # dedicated stem kernel layout ([7][4][64][8]) when the first conv is the torchvision 7x7/2 stem
         st = units[0]
         self.stem4_ok = (st.kind == "conv" and st.k == 7 and st.stride == 2 and st.pad == 3 and st.cin <= 4 and
@@ -316,7 +317,7 @@ class Engine(object):
     def prep_weights(self, flat, wset, want_dgrad):
         """fp32 master (flat vector) -> bf16 tensor-core layouts of every conv / linear, one launch."""
         desc = wset.desc_with_dgrad if (want_dgrad and wset.pool_d is not None) else wset.desc_fprop_only
-        ops.prep_weights_multi(flat, wset.pool_f, wset.pool_d, desc)
+        ops.prep_weights_multi(flat, wset.pool_f, wset.pool_d, desc, wset.prep_blocks)
         if wset.stem4_ok:
             st = self.stem
             ops.prep_weight_stem4(flat[st.w_off:st.w_off + st.w_numel].view(st.cout, st.cin, st.k, st.k),

@@ -134,10 +134,18 @@ def prep_weight_fold(w, out_f=None):
     return out_f
 
 
-def prep_weights_multi(flat, pool_f, pool_d, desc):
-    """All weights of one parameter set (flat fp32 vector) -> bf16 tensor-core layouts, one launch."""
-    check(lib.byol_prep_weights_multi(_ptr(flat), _ptr(pool_f), _ptr(pool_d), _ptr(desc), desc.shape[0], _stream()),
-          "byol_prep_weights_multi")
+def prep_weights_multi(flat, pool_f, pool_d, desc, num_blocks=None):
+    """All weights of one parameter set (flat fp32 vector) -> bf16 tensor-core layouts, one launch.
+    num_blocks: sum of prep_unit_blocks over the rows of `desc` (computed from the device table when not given)."""
+    if num_blocks is None:
+        num_blocks = prep_blocks(desc.cpu().tolist())
+    check(lib.byol_prep_weights_multi(_ptr(flat), _ptr(pool_f), _ptr(pool_d), _ptr(desc), desc.shape[0], num_blocks,
+                                      _stream()), "byol_prep_weights_multi")
+
+
+def prep_blocks(rows):
+    """Grid size for prep_weights_multi: rows = [[src, dstf, dstd, Cout, Cin, Cpad, taps, fold], ...]."""
+    return sum(lib.byol_prep_unit_blocks(int(r[3]), int(r[4]), int(r[5]), int(r[6]), int(r[7])) for r in rows)
 
 
 def cast_bf16_pitched(x2d, ldy):

@@ -119,8 +119,9 @@ int byol_prep_weight(const float* w, void* w_fprop, void* w_dgrad, int Cout, int
 int byol_prep_weight_fold(const float* w, void* w_fprop, int Cout, int Cin, int KH, int KW, byol_stream_t stream);
 /* every conv / linear weight of one parameter set in one launch; desc: device int64 [num_units][8] =
  * {src offset in flat, fprop offset in pool_f, dgrad offset in pool_d or -1, Cout, Cin, Cpad, taps, fold (KH*16+KW or 0)} */
+int byol_prep_unit_blocks(int Cout, int Cin, int Cpad, int taps, int fold);   /* blocks one unit needs */
 int byol_prep_weights_multi(const float* flat, void* pool_f, void* pool_d, const int64_t* desc, int num_units,
-                            byol_stream_t stream);
+                            int num_blocks /* sum of byol_prep_unit_blocks over the units */, byol_stream_t stream);
 /* y[n,i,j,:] = x[n,2i,2j,:] (input of a 1x1 / stride-2 downsample conv, compacted for the TMA-fed GEMM) */
 int byol_subsample2(const void* x, void* y, int N, int H, int W, int C, byol_stream_t stream);
 int byol_cast_f32_bf16(const float* x, void* y, int64_t n, byol_stream_t stream);
