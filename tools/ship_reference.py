@@ -4,7 +4,7 @@ the GPU box with the gpurun snapshot (/root/reference itself does not exist ther
 
     python tools/ship_reference.py
 
-Used by tests/test_gpu_dropin.py (the byol_b200 classes dropped into the reference's own main.execute_graph) and
+Used by tests/test_gpu_zz_dropin.py (the byol_b200 classes dropped into the reference's own main.execute_graph) and
 tools/ref_gpu_baseline.py (the reference's stock PyTorch path timed on the same GPUs).  Nothing is modified; the
 missing `helpers` / `datasets` / `tree` submodules come from oracle/ref_shims at import time.  baseline/_ref/ is
 never committed (.gitignore) — reference sources stay out of this repository's history.
