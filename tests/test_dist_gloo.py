@@ -18,7 +18,10 @@ def _worker(rank, world, port, ret):
     g = torch.Generator().manual_seed(100 + rank)
     x = torch.randn(16, 8, generator=g)
     stats = torch.cat([x.sum(0), (x * x).sum(0)])
-    comm.allreduce_sum_(stats)
+    local = torch.empty_like(stats)
+    comm.allreduce_sum_(stats, local_out=local, channel=1)      # CPU tensors: the gloo path; local_out = the input
+    assert torch.equal(local, torch.cat([x.sum(0), (x * x).sum(0)]))
+    assert comm.peer_exchange(torch.device("cpu")) is None       # the NVLink peer exchange needs NCCL + CUDA
     # (2) DDP: MEAN of the flat gradient
     grad = torch.full((1000,), float(rank + 1))
     comm.allreduce_mean_(grad)
