@@ -90,9 +90,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded spin: a pipeline bug traps (reported as a launch failure) instead of
 // hanging the GPU.  try_wait suspends in hardware, so the bound is generous.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // (2^28 polls: waits that span a grid barrier plus a cross-rank exchange — the MMA warp of mlp_fused_fwd_kernel under
+  // SyncBatchNorm — can legitimately last as long as the rank skew, e.g. right after the CUDA-graph capture)
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
+    if (++spins > (1u << 28)) __trap();
   }
 }
 
